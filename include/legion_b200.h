@@ -1,0 +1,259 @@
+/*
+ * legion_b200.h — C ABI of liblegion_b200.so: Legion's mini-batch data path
+ * (k-hop neighbour sampling + unified-cache lookup + feature gather) for B200.
+ *
+ * This is the drop-in boundary.  Every entry point below replaces one piece of the
+ * reference's operator FFI (the five `extern "C"` op bodies declared in
+ * sampling_server/src/engine/operator_impl.cuh:11-63) or of the cache / storage code
+ * those bodies call.  Where the reference passes C++ object pointers (MemoryPool*,
+ * UnifiedCache*, GraphStorage*) this ABI passes flat descriptors of raw device
+ * pointers and sizes, so it can be bound from C++, ctypes, cgo, JNI …
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from lg_last_error() (thread local).  The reference exits the process on
+ *     any CUDA error (engine/operator_impl.cu:16-24); the host layer above this ABI keeps
+ *     that behaviour, the ABI itself never calls exit().
+ *   - `stream` is a cudaStream_t passed as void*.  Everything is enqueued on it; no call
+ *     synchronises the device unless its comment says so (the reference performs >= 5
+ *     blocking cudaMemcpy per hop: engine/operator_impl.cu:439-445, cache/cache.cu:187-188).
+ *   - the caller owns every buffer it passes in; handles own only their private scratch.
+ *   - one host thread per GPU drives one lg_sampler (engine/server.cu:122-130).
+ */
+#ifndef LEGION_B200_H_
+#define LEGION_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants shared with the reference wire format (include/system_config.cuh:47-57) ---- */
+#define LG_INTERBATCH_CON 2   /* pipeline slots per GPU                     */
+#define LG_INTRABATCH_CON 3   /* ops per hop (sample, lookup, io)           */
+#define LG_MAX_DEVICE 8
+#define LG_MEMORY_USAGE 7     /* IPC buffers per (gpu, slot)                */
+#define LG_COUNTER_SLOTS 16   /* int32 node_counter[16], edge_counter[16]   */
+#define LG_CACHEMISS_FLAG (-2)
+#define LG_MAX_HOPS 6         /* nc[9+h] must stay inside 16 slots          */
+#define LG_TRAINMODE 0
+#define LG_VALIDMODE 1
+#define LG_TESTMODE 2
+
+/* random streams for the neighbour pick */
+#define LG_RNG_MINSTD 0 /* thrust::minstd_rand seed 1, discard(slot) — the reference stream
+                           (engine/operator_impl.cu:235-238)                              */
+#define LG_RNG_PHILOX 1 /* Philox4x32-10, key=(seed lo,hi), ctr=(slot, hop, batch, stream) */
+
+/* data movers of the gather */
+#define LG_GATHER_AUTO 0
+#define LG_GATHER_LDG 1 /* warp-per-row 16-byte ld.global.nc / st.global */
+#define LG_GATHER_TMA 2 /* cp.async.bulk row loads into smem + bulk tile store */
+
+typedef void* lg_stream_t;
+typedef struct lg_sampler lg_sampler;
+
+/* ---- descriptors (plain structs of device pointers; passed by const pointer, copied) ---- */
+
+/* CSR pointer tables: replaces GraphStorage's per-GPU table of P+1 pointer pairs
+ * (storage/graph_storage.cu:30-33,60-62,162-167).  Slots 0..n_parts-1 are the cached CSR
+ * shards of the NVLink clique (local or peer HBM); slot n_parts is the full CSR (host
+ * pinned via UVA, or HBM when the whole graph is resident).  `directory` replaces the two
+ * bcht maps queried by UnifiedCache::FindTopo (cache/cache.cu:217-225): entry v is
+ * part*shard_rows + row, or LG_CACHEMISS_FLAG.  NULL directory = every vertex misses. */
+typedef struct lg_topology {
+  int32_t n_parts;
+  int32_t shard_rows; /* edge_capacity_ (rows per shard) */
+  int64_t num_nodes;
+  const int64_t* indptr[LG_MAX_DEVICE + 1];
+  const int32_t* indices[LG_MAX_DEVICE + 1];
+  const int32_t* directory;
+} lg_topology;
+
+/* Feature cache: replaces float** gpu_float_feature + cpu_float_features + node_map_
+ * (cache/cache.cu:572-602, cache/cache_impl.cuh:239-272).  directory[v] = gidx =
+ * part*shard_rows + row (cache_impl.cuh:104-109) or LG_CACHEMISS_FLAG. */
+typedef struct lg_feature_cache {
+  int32_t n_parts;
+  int32_t shard_rows; /* node_capacity_ (rows per shard) */
+  int32_t dim;        /* float_feature_len */
+  int32_t reserved;
+  int64_t num_nodes;
+  const float* shard[LG_MAX_DEVICE];
+  const float* backing;     /* full [num_nodes x dim] matrix: host UVA pointer or HBM */
+  const int32_t* directory; /* NULL = every row misses */
+} lg_feature_cache;
+
+/* The seven per-(gpu, slot) buffers the trainer opens over CUDA IPC
+ * (engine/ipc_service.cu:134-206; training_backend/ipc_cuda_kernel.cu:62-68). */
+typedef struct lg_batch {
+  int32_t* ids;          /* [num_ids]   global ids, seeds first                  */
+  float* features;       /* [feature_rows x dim]                                 */
+  int32_t* labels;       /* [batch]                                              */
+  int32_t* agg_src;      /* [num_ids]   batch-local index of sampled neighbour   */
+  int32_t* agg_dst;      /* [num_ids]   batch-local index of the frontier vertex */
+  int32_t* node_counter; /* [16]        protocol: SURVEY 3.3 / operator_impl.cu:57-89 */
+  int32_t* edge_counter; /* [16]                                                 */
+  int64_t feature_rows;  /* capacity of `features` in rows (reference: 1.2 x presampled max, unchecked) */
+  int32_t num_ids;       /* capacity of ids / agg_src / agg_dst                  */
+  int32_t reserved;
+} lg_batch;
+
+/* ---- library ---- */
+const char* lg_last_error(void);
+int lg_version(void);
+/* bytes / counts a host needs to size things without guessing */
+int64_t lg_num_ids(int32_t batch_size, const int32_t* fanout, int32_t n_hops); /* engine/server.cu:187-199 */
+
+/* ---- sampler handle: private scratch (dedup table, scan state, global-id frontier) ---- */
+int lg_sampler_create(int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
+                      lg_sampler** out);
+int lg_sampler_destroy(lg_sampler* s);
+/* dedup-table slots (power of two) — exposed for tests of the collision path */
+int lg_sampler_set_table_slots(lg_sampler* s, int64_t slots);
+int64_t lg_sampler_scratch_bytes(const lg_sampler* s);
+/* data mover used by lg_feature_cache_lookup: LG_GATHER_AUTO / LG_GATHER_LDG / LG_GATHER_TMA */
+int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant);
+/* sticky overflow status (0 ok, 1 ids overflow, 2 features buffer too small — the reference
+ * sizes it 1.2 x presampled max without a bound check, engine/server.cu:277).  Synchronises. */
+int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);
+
+/* ---- the five operator bodies (engine/operator_impl.cuh:11-63) ---- */
+
+/* BatchGenerate (engine/operator_impl.cu:27-55,92-172): seeds of batch `counter` =
+ * all_ids[batch_size*counter ...], -1 past total_cap; labels; counters reset + op-0 update;
+ * seeds enter the dedup table with local index = position. */
+int lg_batch_generate(lg_sampler* s, lg_stream_t stream, const int32_t* all_ids,
+                      const int32_t* all_labels, int32_t total_cap, int32_t batch_size,
+                      int32_t counter, const lg_batch* batch);
+
+/* RandomSample (engine/operator_impl.cu:175-296,400-499): one hop.  hop is 1-based
+ * (op_id = 3*hop).  Slot rule, with-replacement pick, first-seen dedup, local re-indexing
+ * (construct_graph) and the op's counter_update are all done on the device; output order is
+ * ascending slot index.  edge_hotness (u64[num_nodes], may be NULL) receives the
+ * presampling count of engine/operator_impl.cu:358. */
+int lg_random_sample(lg_sampler* s, lg_stream_t stream, const lg_topology* topo, int32_t hop,
+                     int32_t rng_kind, uint64_t rng_seed, uint32_t batch_id, uint32_t stream_id,
+                     const lg_batch* batch, unsigned long long* edge_hotness);
+
+/* FeatureCacheLookup (engine/operator_impl.cu:501-519 -> cache/cache.cu:180-215,726-748 ->
+ * cache/cache_impl.cuh:239-272): counter snapshot for op_id, directory lookup (FindFeat) and
+ * gather of rows [nc[2], nc[2]+nc[3]) of `ids` into batch->features.  tier_rows (u64[3],
+ * may be NULL) accumulates local / peer / miss row counts (hit-mix telemetry). */
+int lg_feature_cache_lookup(lg_sampler* s, lg_stream_t stream, const lg_feature_cache* cache,
+                            int32_t op_id, int32_t local_part, const lg_batch* batch,
+                            unsigned long long* tier_rows);
+
+/* IOSubmit is a no-op in the reference (engine/operator_impl.cu:521-539); kept for API parity. */
+int lg_io_submit(lg_sampler* s, lg_stream_t stream, int32_t op_id, const lg_batch* batch);
+
+/* IOComplete (engine/operator_impl.cu:542-580): train mode only — end-of-batch cleanup
+ * (ClearPosMap equivalent) and, when node_hotness != NULL, HotnessMeasure
+ * (cache/cache_impl.cuh:190-198) plus the running max of unique ids (cache/cache.cu:59-61,
+ * written to max_ids, a device int32, may be NULL). */
+int lg_io_complete(lg_sampler* s, lg_stream_t stream, int32_t mode, const lg_batch* batch,
+                   unsigned long long* node_hotness, int32_t* max_ids);
+
+/* ---- fused batch: ops 0..3*hops+3 back to back on one stream (GPURunner::RunOnce body,
+ *      engine/server.cu:311-317) ---- */
+typedef struct lg_batch_params {
+  const int32_t* all_ids;    /* device */
+  const int32_t* all_labels; /* device */
+  int32_t total_cap;
+  int32_t batch_size;
+  int32_t counter; /* local batch id */
+  int32_t mode;
+  int32_t rng_kind;
+  uint32_t batch_id; /* global batch id (Philox ctr word 2) */
+  uint32_t stream_id; /* GPU / rank (Philox ctr word 3) */
+  int32_t local_part; /* this GPU's slot in the clique */
+  uint64_t rng_seed;
+} lg_batch_params;
+
+int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
+                 const lg_feature_cache* cache, const lg_batch_params* p, const lg_batch* batch,
+                 unsigned long long* tier_rows);
+
+/* End-to-end form with HOST buffers (pinned or pageable): H2D of the seed ids + labels of
+ * this batch, lg_run_batch, D2H of both counter arrays (what get_next reads:
+ * training_backend/ipc_cuda_kernel.cu:194-195).  Synchronises `stream` before returning. */
+int lg_run_batch_host(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
+                      const lg_feature_cache* cache, const lg_batch_params* p,
+                      const int32_t* host_seed_ids, const int32_t* host_seed_labels,
+                      const lg_batch* batch, int32_t* host_node_counter,
+                      int32_t* host_edge_counter);
+
+/* ---- standalone gather (the roofline kernel) : dst[r,:] = row of ids[r] for r in [0,n) ---- */
+int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache, const int32_t* ids,
+                   int64_t n, float* dst, int32_t local_part, int32_t variant,
+                   unsigned long long* tier_rows);
+
+/* ---- unified cache construction (cache/cache.cu:360-443,71-136,553-611) ---- */
+
+/* aggregate_access (cache/cache_impl.cuh:72-76): agg[i] += part[i]; `part` may be peer memory */
+int lg_hotness_accumulate(lg_stream_t stream, unsigned long long* agg,
+                          const unsigned long long* part, int64_t n);
+/* CandidateSelection ranking (cache/cache.cu:414-415,434-435): order = ids sorted by hotness
+ * descending, ties by ascending id (the reference's thrust sort leaves ties unspecified).
+ * sorted_hotness may be NULL.  tmp/tmp_bytes: pass tmp=NULL to query the size. */
+int lg_hotness_rank(lg_stream_t stream, const unsigned long long* hotness, int64_t n,
+                    int32_t* order, unsigned long long* sorted_hotness, void* tmp,
+                    int64_t* tmp_bytes);
+/* InitPair + insert (cache/cache_impl.cuh:104-109; cache/cache.cu:94-102): for rank r in
+ * [0, cap*kg): directory[order[r]] = (r % kg)*cap + r/kg.  directory must be pre-filled with
+ * LG_CACHEMISS_FLAG (lg_fill_i32). */
+int lg_place_features(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg,
+                      int64_t num_nodes, int32_t* directory);
+/* InitIndexPair/InitOffsetPair + insert (cache/cache_impl.cuh:89-101): part = r%kg + ki*kg,
+ * row = r/kg, stored packed as part*cap + row. */
+int lg_place_topology(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg,
+                      int32_t ki, int64_t num_nodes, int32_t* directory);
+/* FeatFillUp (cache/cache_impl.cuh:183-188): shard[r,:] = backing[order[r*kg + j],:] */
+int lg_fill_feature_shard(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg,
+                          int32_t j, int32_t dim, int64_t num_nodes, const float* backing,
+                          float* shard);
+/* GraphCache (storage/graph_storage.cu:76-111; graph_storage_impl.cuh:33-53), two calls:
+ * counts -> shard_indptr[cap+1] (exclusive scan, shard_indptr[cap] = total edges), then fill. */
+int lg_topo_shard_indptr(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg,
+                         int32_t j, int64_t num_nodes, const int64_t* indptr,
+                         int64_t* shard_indptr);
+int lg_topo_shard_fill(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg,
+                       int32_t j, int64_t num_nodes, const int64_t* indptr,
+                       const int32_t* indices, const int64_t* shard_indptr,
+                       int32_t* shard_indices);
+int lg_fill_i32(lg_stream_t stream, int32_t* dst, int32_t value, int64_t n);
+
+/* CostModel (cache/cache.cu:445-551), host arithmetic on host arrays: picks the feature /
+ * topology split.  sorted_*_hotness are the descending arrays from lg_hotness_rank copied to
+ * the host; topo_order is the topology ranking; indptr the full CSR offsets (host).
+ * topo_trans / feat_trans are the measured transaction totals (reference: PCM counters,
+ * always 0 — engine/server.cu:106).  Outputs capacities per GPU (rows). */
+int lg_cost_model(const unsigned long long* sorted_node_hotness,
+                  const unsigned long long* sorted_edge_hotness, const int32_t* topo_order,
+                  const int64_t* indptr, int64_t num_nodes, int32_t dim, int64_t cache_bytes,
+                  int32_t kg, uint64_t topo_trans, uint64_t feat_trans, int32_t* node_capacity,
+                  int32_t* edge_capacity, double* alpha);
+
+/* ---- device plumbing a non-CUDA host needs (storage/storage_management.cu:5-23,100-115;
+ *      engine/ipc_service.cu:163-169; training_backend/ipc_cuda_kernel.cu:62-68) ---- */
+int lg_device_count(int32_t* n);
+int lg_set_device(int32_t device);
+int lg_enable_peer_access(int32_t n_devices);
+int lg_device_alloc(void** ptr, int64_t bytes); /* plain cudaMalloc: legacy-IPC exportable */
+int lg_device_free(void* ptr);
+int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t bytes); /* cudaHostAllocMapped */
+int lg_host_free(void* host_ptr);
+int lg_ipc_export(const void* device_ptr, unsigned char handle[64]);
+int lg_ipc_open(const unsigned char handle[64], void** device_ptr);
+int lg_ipc_close(void* device_ptr);
+int lg_stream_create(lg_stream_t* stream);
+int lg_stream_destroy(lg_stream_t stream);
+int lg_stream_synchronize(lg_stream_t stream);
+int lg_memcpy_h2d(void* dst, const void* src, int64_t bytes, lg_stream_t stream);
+int lg_memcpy_d2h(void* dst, const void* src, int64_t bytes, lg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEGION_B200_H_ */

@@ -1,0 +1,135 @@
+// common.cuh — shared device helpers of liblegion_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/legion_b200.h"
+
+int lg_set_error(const char* fmt, ...);
+
+#define LG_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return lg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+  } while (0)
+#define LG_LAUNCH_OK() LG_CUDA(cudaGetLastError())
+#define LG_REQUIRE(cond, ...)                      \
+  do {                                             \
+    if (!(cond)) return lg_set_error(__VA_ARGS__); \
+  } while (0)
+
+typedef unsigned long long u64;
+
+namespace lg {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- Philox4x32-10 (Random123).  ctr = (slot, hop, batch, stream), key = seed ----
+__device__ __forceinline__ uint32_t philox_word0(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+// ---- thrust::minstd_rand seed 1, discard(idx), one draw:  x = 48271^(idx+1) mod (2^31-1)
+//      (reference stream, engine/operator_impl.cu:235-238).  Mersenne fold instead of %. ----
+__device__ __forceinline__ uint32_t mod_m31(u64 x) {
+  x = (x & 0x7FFFFFFFull) + (x >> 31);
+  x = (x & 0x7FFFFFFFull) + (x >> 31);
+  return (x >= 0x7FFFFFFFull) ? (uint32_t)(x - 0x7FFFFFFFull) : (uint32_t)x;
+}
+__device__ __forceinline__ uint32_t minstd_x(uint32_t idx) {
+  u64 mult = 48271ull, acc = 1ull;
+  u64 z = (u64)idx + 1ull;  // discard(idx) then engine() == 48271^(idx+1)
+  while (z) {
+    if (z & 1ull) acc = mod_m31(acc * mult);
+    z >>= 1;
+    mult = mod_m31(mult * mult);
+  }
+  return (uint32_t)acc;
+}
+__device__ __forceinline__ int32_t pick_minstd(uint32_t idx, int32_t deg) {
+  double r = (double)(minstd_x(idx) - 1u);
+  r = __ddiv_rn(r, 2147483646.0);  // uniform_real_distribution: /(1 + (max-min))
+  return (int32_t)__dmul_rn(r, (double)deg);
+}
+
+template <int RNG>
+__device__ __forceinline__ int32_t pick_neighbor(uint32_t slot, int32_t deg, uint32_t hop, uint32_t batch_id,
+                                                 uint32_t stream_id, uint32_t k0, uint32_t k1) {
+  if (RNG == LG_RNG_MINSTD) return pick_minstd(slot, deg);
+  uint32_t r = philox_word0(slot, hop, batch_id, stream_id, k0, k1);
+  return (int32_t)__umulhi(r, (uint32_t)deg);
+}
+
+// ---- relaxed gpu-scope 64-bit accesses (cross-CTA flags and dedup-table words) ----
+__device__ __forceinline__ u64 ld_relaxed(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t hash32(uint32_t k) {  // murmur3 fmix32
+  k ^= k >> 16; k *= 0x85EBCA6Bu; k ^= k >> 13; k *= 0xC2B2AE35u; k ^= k >> 16;
+  return k;
+}
+
+__device__ __forceinline__ int32_t warp_sum(int32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int32_t warp_incl_scan(int32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// ---- single-pass chained scan (decoupled look-back).  state[t] = flag<<32 | value,
+//      flag 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.  Called by one full warp;
+//      tiles are claimed through an atomic ticket so every predecessor is already running. ----
+__device__ __forceinline__ int32_t lookback_exclusive(u64* state, int tile, int32_t aggregate, int lane) {
+  if (tile == 0) {
+    if (lane == 0) st_relaxed(state, (2ull << 32) | (uint32_t)aggregate);
+    return 0;
+  }
+  if (lane == 0) st_relaxed(state + tile, (1ull << 32) | (uint32_t)aggregate);
+  int32_t excl = 0;
+  int look = tile - 1;
+  while (true) {
+    int idx = look - lane;
+    u64 s = (idx >= 0) ? ld_relaxed(state + idx) : (2ull << 32);
+    while (__any_sync(0xffffffffu, (s >> 32) == 0ull)) {
+      if ((s >> 32) == 0ull) s = ld_relaxed(state + idx);
+    }
+    unsigned done = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
+    int32_t v = (int32_t)(uint32_t)s;
+    if (done) {
+      int first = __ffs(done) - 1;
+      excl += warp_sum(lane <= first ? v : 0);
+      break;
+    }
+    excl += warp_sum(v);
+    look -= 32;
+  }
+  if (lane == 0) st_relaxed(state + tile, (2ull << 32) | (uint32_t)(excl + aggregate));
+  return excl;
+}
+
+}  // namespace lg

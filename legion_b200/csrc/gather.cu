@@ -1,0 +1,356 @@
+// gather.cu — unified-cache lookup + feature gather for sm_100a.
+//
+// Replaces  UnifiedCache::FindFeat (bcht probe kernel + blocking D2H, cache/cache.cu:180-215)  and
+// multiGPU_feat_cache_lookup (one thread per float, 4-byte loads, 64-bit div+mod per element,
+// 32 CTAs: cache/cache_impl.cuh:239-272; cache/cache.cu:726-748)  with one launch per op:
+// the location of a row (local HBM shard / peer HBM shard over NVLink / backing matrix in host
+// pinned memory or HBM) is decoded ONCE per row from a dense int32 directory, rows move as
+// 16-byte vectors.  Two data movers:
+//   LDG  — warp per row, R rows in flight per warp, ld.global.nc.L1::no_allocate.v4 -> st.global.v4
+//   TMA  — one warp per CTA; every lane issues a cp.async.bulk (row -> shared memory stage,
+//          mbarrier complete_tx), lane 0 drains a finished stage with ONE bulk store of the
+//          32 contiguous destination rows.  No registers touch the payload (SASS: UBLKCP).
+// Values are moved bit-for-bit (no arithmetic), so the output is bit-exact by construction.
+#include "common.cuh"
+#include "sampler_state.cuh"
+
+using namespace lg;
+
+namespace {
+
+struct GatherArgs {
+  lg_feature_cache cache;
+  const int32_t* ids;  // row r reads ids[off + r]
+  float* dst;          // row r writes dst[(off + r) * dim ...]
+  int32_t* nc;         // non-null: (off, cnt) come from the counter protocol for `hop`
+  int64_t off, cnt;    // used when nc == null
+  int64_t dst_rows;    // capacity of dst in rows
+  int32_t hop;         // op_id / 3
+  int32_t op_slot;     // op_id % 3 (snapshot slot, engine/operator_impl.cu:83-85)
+  int32_t local_part;
+  u64* tier;           // [3] local / peer / miss rows, may be null
+  int32_t* status;
+};
+
+__device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int64_t* cnt) {
+  if (a.nc) {
+    // rows of hop h are [nc[9+h-1], nc[9+h]) — identical to (nc[0], nc[1]) right after op 3h
+    // (engine/operator_impl.cu:65-81) but immutable afterwards, so a later hop may already run.
+    int32_t lo = a.hop == 0 ? 0 : a.nc[LG_INTRABATCH_CON * 3 + a.hop - 1];
+    int32_t hi = a.nc[LG_INTRABATCH_CON * 3 + a.hop];
+    *off = lo;
+    *cnt = hi - lo;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the op's counter_update (:83-85)
+      a.nc[a.op_slot * 2] = lo;
+      a.nc[a.op_slot * 2 + 1] = hi - lo;
+    }
+  } else {
+    *off = a.off;
+    *cnt = a.cnt;
+  }
+}
+
+// location decode: returns the source row pointer or nullptr (row is skipped), tier in *t
+__device__ __forceinline__ const float* locate(const GatherArgs& a, int32_t id, int* t) {
+  *t = -1;
+  if (id < 0) return nullptr;  // -1 padding of a tail batch (cache_impl.cuh:263-264)
+  int32_t gidx = LG_CACHEMISS_FLAG;
+  if (a.cache.directory && id < a.cache.num_nodes) gidx = a.cache.directory[id];
+  if (gidx < 0) {  // miss -> backing matrix (cache_impl.cuh:262-266)
+    *t = 2;
+    return a.cache.backing + (int64_t)(id % a.cache.num_nodes) * a.cache.dim;
+  }
+  int32_t didx = gidx / a.cache.shard_rows;  // cache_impl.cuh:259-260
+  int32_t fidx = gidx - didx * a.cache.shard_rows;
+  *t = (didx == a.local_part) ? 0 : 1;
+  return a.cache.shard[didx] + (int64_t)fidx * a.cache.dim;
+}
+
+__device__ __forceinline__ float4 ld_nc_v4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_v4(float* p, const float4& v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void tier_flush(const GatherArgs& a, int32_t t0, int32_t t1, int32_t t2, int lane) {
+  if (!a.tier) return;
+  t0 = warp_sum(t0);
+  t1 = warp_sum(t1);
+  t2 = warp_sum(t2);
+  if (lane == 0) {
+    if (t0) atomicAdd(a.tier + 0, (u64)t0);
+    if (t1) atomicAdd(a.tier + 1, (u64)t1);
+    if (t2) atomicAdd(a.tier + 2, (u64)t2);
+  }
+}
+
+// ---------------- LDG mover: warp per R consecutive rows ----------------
+template <int R, bool VEC4>
+__global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
+  int64_t off, cnt;
+  row_range(a, &off, &cnt);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int dim = a.cache.dim;
+  int32_t t0 = 0, t1 = 0, t2 = 0;
+  for (int64_t r0 = warp_global * R; r0 < cnt; r0 += n_warps * R) {
+    const float* src = nullptr;
+    if (lane < R && r0 + lane < cnt) {
+      int64_t row = off + r0 + lane;
+      if (row < a.dst_rows) {
+        int t;
+        src = locate(a, a.ids[row], &t);
+        t0 += (t == 0);
+        t1 += (t == 1);
+        t2 += (t == 2);
+      } else {
+        *a.status = 2;
+      }
+    }
+    if (VEC4) {
+      const int d4 = dim >> 2;
+      for (int c0 = 0; c0 < d4; c0 += 32) {
+        const int c = c0 + lane;
+        float4 v[R];
+        const float* sk[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          sk[k] = (const float*)__shfl_sync(0xffffffffu, (u64)src, k);
+          if (sk[k] && c < d4) v[k] = ld_nc_v4(sk[k] + 4 * c);
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++)
+          if (sk[k] && c < d4) st_v4(a.dst + (off + r0 + k) * dim + 4 * c, v[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        const float* s = (const float*)__shfl_sync(0xffffffffu, (u64)src, k);
+        if (!s) continue;
+        float* d = a.dst + (off + r0 + k) * dim;
+        for (int c = lane; c < dim; c += 32) d[c] = __ldg(s + c);
+      }
+    }
+  }
+  tier_flush(a, t0, t1, t2, lane);
+}
+
+// ---------------- TMA mover: bulk async copies through shared memory ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kTmaRows = 32;  // rows per stage == lanes
+// Pipeline: iteration `it` fills stage it % STAGES with tile(it) and drains tile(it - LAG),
+// LAG = STAGES - 2: LAG tiles of row loads in flight, one stage being stored, one being refilled.
+template <int STAGES>
+__global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
+  static_assert(STAGES >= 3, "need a stage in store and a stage in refill besides the loads in flight");
+  constexpr int LAG = STAGES - 2;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) u64 bars[STAGES];
+  __shared__ unsigned s_valid[STAGES];
+  int64_t off, cnt;
+  row_range(a, &off, &cnt);
+  const int lane = threadIdx.x;
+  const uint32_t row_bytes = (uint32_t)a.cache.dim * 4u;
+  const uint32_t stage_bytes = row_bytes * kTmaRows;
+  const int64_t n_tiles = (cnt + kTmaRows - 1) / kTmaRows;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  int32_t t0 = 0, t1 = 0, t2 = 0;
+  int64_t my_tiles = 0;
+  if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  for (int64_t it = 0; it < my_tiles + LAG; it++) {
+    if (it < my_tiles) {
+      const int s = (int)(it % STAGES);
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t row = off + tile * kTmaRows + lane;
+      // stage s was read by the store of tile(it - STAGES), issued two iterations ago: only the
+      // store issued in the previous iteration may still be reading shared memory
+      bulk_wait_read<1>();
+      __syncwarp();
+      const float* src = nullptr;
+      if (tile * kTmaRows + lane < cnt) {
+        if (row < a.dst_rows) {
+          int t;
+          src = locate(a, a.ids[row], &t);
+          t0 += (t == 0);
+          t1 += (t == 1);
+          t2 += (t == 2);
+        } else {
+          *a.status = 2;
+        }
+      }
+      const unsigned valid = __ballot_sync(0xffffffffu, src != nullptr);
+      const uint32_t bar = smem_u32(&bars[s]);
+      if (lane == 0) {
+        s_valid[s] = valid;
+        mbar_expect_tx(bar, row_bytes * (uint32_t)__popc(valid));
+      }
+      __syncwarp();
+      if (src) bulk_g2s(smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), src, row_bytes, bar);
+    }
+    const int64_t dt = it - LAG;
+    if (dt >= 0 && dt < my_tiles) {
+      const int s = (int)(dt % STAGES);
+      const uint32_t parity = (uint32_t)((dt / STAGES) & 1);
+      const int64_t tile = blockIdx.x + dt * gridDim.x;
+      const int64_t row0 = off + tile * kTmaRows;
+      const unsigned valid = s_valid[s];
+      mbar_wait(smem_u32(&bars[s]), parity);
+      const int64_t left = cnt - tile * kTmaRows;
+      const int rows_here = left < kTmaRows ? (int)left : kTmaRows;
+      const unsigned want = (rows_here >= 32) ? 0xffffffffu : ((1u << rows_here) - 1u);
+      if (valid == want) {
+        // every row of the tile is present: the destination rows are contiguous -> ONE bulk store
+        if (lane == 0) bulk_s2g(a.dst + row0 * a.cache.dim, smem_u32(smem + (size_t)s * stage_bytes),
+                                row_bytes * (uint32_t)rows_here);
+      } else if (valid & (1u << lane)) {  // holes (-1 padded seeds): row-wise stores
+        bulk_s2g(a.dst + (row0 + lane) * a.cache.dim,
+                 smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), row_bytes);
+      }
+      bulk_commit();  // every lane commits one (possibly empty) group per drained tile
+      __syncwarp();
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  tier_flush(a, t0, t1, t2, lane);
+}
+
+constexpr int kTmaStages = 4;
+
+int launch_gather(cudaStream_t st, const GatherArgs& a, int variant, int64_t max_rows) {
+  const int dim = a.cache.dim;
+  const bool vec_ok = (dim % 4 == 0) && (((uintptr_t)a.dst & 15) == 0) && (((uintptr_t)a.cache.backing & 15) == 0);
+  if (variant == LG_GATHER_AUTO) variant = LG_GATHER_LDG;
+  if (variant == LG_GATHER_TMA && vec_ok && (size_t)dim * 4 * kTmaRows * kTmaStages <= 200 * 1024) {
+    const size_t smem = (size_t)dim * 4 * kTmaRows * kTmaStages;
+    LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<kTmaStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (ctas_per_sm > 16) ctas_per_sm = 16;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int64_t tiles = (max_rows + kTmaRows - 1) / kTmaRows;
+    int64_t grid = (int64_t)kSMs * ctas_per_sm;
+    if (tiles < grid) grid = tiles > 0 ? tiles : 1;
+    gather_tma_kernel<kTmaStages><<<(int)grid, 32, smem, st>>>(a);
+    LG_LAUNCH_OK();
+    return 0;
+  }
+  constexpr int R = 4;
+  int64_t warps = (max_rows + R - 1) / R;
+  int64_t grid = (warps + 7) / 8;
+  const int64_t cap = (int64_t)kSMs * 8;  // 8 CTAs x 8 warps per SM: full occupancy, grid-stride beyond
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  if (vec_ok)
+    gather_ldg_kernel<R, true><<<(int)grid, 256, 0, st>>>(a);
+  else
+    gather_ldg_kernel<R, false><<<(int)grid, 256, 0, st>>>(a);
+  LG_LAUNCH_OK();
+  return 0;
+}
+
+int check_cache(const lg_feature_cache* c) {
+  LG_REQUIRE(c, "feature cache descriptor is null");
+  LG_REQUIRE(c->dim > 0, "feature cache: dim %d", c->dim);
+  LG_REQUIRE(c->backing, "feature cache: backing matrix is null");
+  LG_REQUIRE(c->n_parts >= 0 && c->n_parts <= LG_MAX_DEVICE, "feature cache: n_parts %d", c->n_parts);
+  LG_REQUIRE(!c->directory || c->shard_rows > 0, "feature cache: directory without shard_rows");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int lg_feature_cache_lookup(lg_sampler* s, lg_stream_t stream, const lg_feature_cache* cache,
+                                       int32_t op_id, int32_t local_part, const lg_batch* b,
+                                       unsigned long long* tier_rows) {
+  LG_REQUIRE(s && b, "lg_feature_cache_lookup: null argument");
+  int rc = check_cache(cache);
+  if (rc) return rc;
+  LG_REQUIRE(op_id % LG_INTRABATCH_CON == 1, "lg_feature_cache_lookup: op_id %d is not a lookup op", op_id);
+  LG_REQUIRE(b->features, "lg_feature_cache_lookup: features buffer is null");
+  GatherArgs a;
+  a.cache = *cache;
+  a.ids = b->ids;
+  a.dst = b->features;
+  a.nc = b->node_counter;
+  a.off = 0;
+  a.cnt = 0;
+  a.dst_rows = b->feature_rows;
+  a.hop = op_id / LG_INTRABATCH_CON;
+  a.op_slot = op_id % LG_INTRABATCH_CON;
+  a.local_part = local_part;
+  a.tier = (u64*)tier_rows;
+  a.status = s->status;
+  LG_REQUIRE(a.hop <= s->n_hops, "lg_feature_cache_lookup: op_id %d beyond %d hops", op_id, s->n_hops);
+  return launch_gather((cudaStream_t)stream, a, s->gather_variant, s->slots_per_hop[a.hop]);
+}
+
+extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache, const int32_t* ids, int64_t n,
+                              float* dst, int32_t local_part, int32_t variant, unsigned long long* tier_rows) {
+  int rc = check_cache(cache);
+  if (rc) return rc;
+  LG_REQUIRE(ids && dst, "lg_gather_rows: null argument");
+  if (n <= 0) return 0;
+  static thread_local int32_t* dummy_status = nullptr;
+  if (!dummy_status) LG_CUDA(cudaMalloc(&dummy_status, sizeof(int32_t)));
+  GatherArgs a;
+  a.cache = *cache;
+  a.ids = ids;
+  a.dst = dst;
+  a.nc = nullptr;
+  a.off = 0;
+  a.cnt = n;
+  a.dst_rows = n;
+  a.hop = 0;
+  a.op_slot = 0;
+  a.local_part = local_part;
+  a.tier = (u64*)tier_rows;
+  a.status = dummy_status;
+  return launch_gather((cudaStream_t)stream, a, variant, n);
+}

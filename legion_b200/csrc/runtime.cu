@@ -1,0 +1,114 @@
+// runtime.cu — error reporting and the thin device plumbing a non-CUDA host needs
+// (storage/storage_management.cu:5-23,100-115; engine/ipc_service.cu:163-169;
+//  training_backend/ipc_cuda_kernel.cu:62-68).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+int lg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+extern "C" const char* lg_last_error(void) { return g_err; }
+extern "C" int lg_version(void) { return 100; }
+
+extern "C" int lg_device_count(int32_t* n) {
+  LG_REQUIRE(n, "null");
+  int c = 0;
+  LG_CUDA(cudaGetDeviceCount(&c));
+  *n = c;
+  return 0;
+}
+extern "C" int lg_set_device(int32_t device) {
+  LG_CUDA(cudaSetDevice(device));
+  return 0;
+}
+extern "C" int lg_enable_peer_access(int32_t n_devices) {
+  int cur = 0;
+  LG_CUDA(cudaGetDevice(&cur));
+  for (int i = 0; i < n_devices; i++) {
+    LG_CUDA(cudaSetDevice(i));
+    for (int j = 0; j < n_devices; j++) {
+      if (i == j) continue;
+      int ok = 0;
+      LG_CUDA(cudaDeviceCanAccessPeer(&ok, i, j));
+      if (!ok) continue;
+      cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        continue;
+      }
+      LG_CUDA(e);
+    }
+  }
+  LG_CUDA(cudaSetDevice(cur));
+  return 0;
+}
+extern "C" int lg_device_alloc(void** ptr, int64_t bytes) {
+  LG_REQUIRE(ptr && bytes >= 0, "lg_device_alloc: bad argument");
+  LG_CUDA(cudaMalloc(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+  return 0;
+}
+extern "C" int lg_device_free(void* ptr) {
+  LG_CUDA(cudaFree(ptr));
+  return 0;
+}
+extern "C" int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t bytes) {
+  LG_REQUIRE(host_ptr && bytes >= 0, "lg_host_alloc_mapped: bad argument");
+  LG_CUDA(cudaHostAlloc(host_ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocMapped | cudaHostAllocPortable));
+  if (device_ptr) LG_CUDA(cudaHostGetDevicePointer(device_ptr, *host_ptr, 0));
+  return 0;
+}
+extern "C" int lg_host_free(void* host_ptr) {
+  LG_CUDA(cudaFreeHost(host_ptr));
+  return 0;
+}
+extern "C" int lg_ipc_export(const void* device_ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes on the wire (shmStruct)");
+  LG_REQUIRE(device_ptr && handle, "lg_ipc_export: null argument");
+  cudaIpcMemHandle_t h;
+  LG_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+  memcpy(handle, &h, 64);
+  return 0;
+}
+extern "C" int lg_ipc_open(const unsigned char handle[64], void** device_ptr) {
+  LG_REQUIRE(device_ptr && handle, "lg_ipc_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  LG_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+extern "C" int lg_ipc_close(void* device_ptr) {
+  LG_CUDA(cudaIpcCloseMemHandle(device_ptr));
+  return 0;
+}
+extern "C" int lg_stream_create(lg_stream_t* stream) {
+  LG_REQUIRE(stream, "null");
+  cudaStream_t s;
+  LG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (lg_stream_t)s;
+  return 0;
+}
+extern "C" int lg_stream_destroy(lg_stream_t stream) {
+  LG_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lg_stream_synchronize(lg_stream_t stream) {
+  LG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lg_memcpy_h2d(void* dst, const void* src, int64_t bytes, lg_stream_t stream) {
+  LG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lg_memcpy_d2h(void* dst, const void* src, int64_t bytes, lg_stream_t stream) {
+  LG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}

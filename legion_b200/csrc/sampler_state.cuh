@@ -1,0 +1,33 @@
+// sampler_state.cuh — private state of an lg_sampler handle (shared by sampler.cu and gather.cu).
+#pragma once
+#include "common.cuh"
+
+struct HopState {  // zeroed once per batch (one cudaMemsetAsync over the whole small region)
+  int32_t sample_ticket;
+  int32_t rank_ticket;
+  int32_t rank_done;
+  int32_t new_nodes;  // C_h, written by the last rank tile
+};
+
+struct lg_sampler {
+  int32_t device;
+  int32_t max_batch;
+  int32_t n_hops;
+  int32_t gather_variant;
+  int32_t fanout[LG_MAX_HOPS];
+  int64_t slots_per_hop[LG_MAX_HOPS + 1];  // S_0 = batch, S_h = S_{h-1} * fanout_h
+  int64_t num_ids;
+  int64_t table_slots;
+  u64* table;            // dedup table: (vertex << 32) | local id, 0xFF..F = empty
+  int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)
+  uint8_t* small;        // memset-per-batch region: HopState[hops] + chained-scan tile states
+  int64_t small_bytes;
+  HopState* hs;
+  u64* sample_state[LG_MAX_HOPS];
+  u64* rank_state[LG_MAX_HOPS];
+  int32_t sample_tiles[LG_MAX_HOPS];
+  int32_t sample_tile_f[LG_MAX_HOPS];
+  int32_t rank_tiles[LG_MAX_HOPS];
+  int32_t* status;       // device int32: 1 = ids overflow, 2 = features buffer overflow
+  int32_t* pinned_seeds;
+};
