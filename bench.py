@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — sampled+gathered seeds/s of the Legion mini-batch data path on B200.
+
+A step = one mini-batch of `batch` seeds through the whole hot path on one GPU: batch_generate ->
+feature gather of the seeds -> per hop (neighbour sampling -> dedup/reindex -> feature gather of the
+new vertices), i.e. the ops of GPURunner::RunOnce (reference engine/server.cu:302-332).
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (N>1: launched by torchrun)
+  python bench.py --impl reference ...                      CPU arm: DGL-semantics sampler + index_select
+                                                            (oracle port) on the host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x1E910
+WORKLOADS = {
+    # name: (shape key, fanout, batch, dmax)
+    "products": ("products", [25, 10], 8000, 20000),
+    "products-small": ("products", [25, 10], 8000, 20000),  # scaled by --scale for smoke runs
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: clocks DURING the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def recorded_traffic():
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# dataset
+# ----------------------------------------------------------------------------------------------
+def shape_of(args):
+    from legion_b200 import synth
+    key, fanout, batch, dmax = WORKLOADS[args.workload]
+    n, e, d, classes = synth.SHAPES[key]
+    n = max(1000, int(n * args.scale))
+    e_target = int(e * args.scale)
+    return dict(name=key, N=n, E_target=e_target, D=d, classes=classes, fanout=fanout, batch=args.batch or batch,
+                dmax=dmax, dmin=synth.dmin_for(n, e_target))
+
+
+def device_dataset(shape, device):
+    """graph + features + labels generated directly in HBM (include/legion_b200_synth.h)"""
+    import torch
+    from legion_b200 import capi
+    L = capi.load()
+    dev = f"cuda:{device}"
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    N, D = shape["N"], shape["D"]
+    ip = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    capi.check(L.lg_synth_indptr(st, N, shape["dmin"], shape["dmax"], SEED, ip.data_ptr()))
+    E = int(ip[N].item())
+    ix = torch.empty(E, dtype=torch.int32, device=dev)
+    capi.check(L.lg_synth_indices(st, N, ip.data_ptr(), SEED, ix.data_ptr()))
+    feat = torch.empty((N, D), dtype=torch.float32, device=dev)
+    capi.check(L.lg_synth_features(st, 0, N, D, SEED, feat.data_ptr()))
+    lab = torch.empty(N, dtype=torch.int32, device=dev)
+    capi.check(L.lg_synth_labels(st, N, shape["classes"], lab.data_ptr()))
+    torch.cuda.synchronize()
+    return ip, ix, feat, lab, E
+
+
+def train_split(shape, world):
+    from legion_b200 import synth
+    tr, _, _ = synth.split_sets(shape["N"], SEED)
+    return synth.partition_ids(tr, world)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from legion_b200 import capi
+    from legion_b200.runner import DataPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"warning: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    capi.load()  # fails loudly if the CUDA library is missing
+
+    shape = shape_of(args)
+    N, D, B, fanout = shape["N"], shape["D"], shape["batch"], shape["fanout"]
+    H = len(fanout)
+    t0 = time.time()
+    ip, ix, feat, lab, E = device_dataset(shape, local)
+    parts = train_split(shape, world)
+    my_train = parts[rank]
+    d_train = torch.from_numpy(my_train).to(dev)
+    d_lab = lab[d_train.long()].contiguous()
+    train_steps = (min(len(p) for p in parts) - 1) // B  # engine/ipc_service.cu:73-82
+    assert train_steps >= 1, "training set smaller than one batch"
+    if rank == 0:
+        log(f"[bench] {shape['name']} N={N} E={E} D={D} world={world} train/gpu={len(my_train)} "
+            f"train_steps={train_steps} setup {time.time() - t0:.1f}s")
+
+    dp = DataPath(local, fanout, B, N, D, rank=rank, world=world)
+    dp.set_full_graph(ip.data_ptr(), ix.data_ptr(), keep=[ip, ix])  # topology replicated in each GPU's HBM
+    dp.set_backing_features(feat.data_ptr(), keep=[feat])
+    dp.set_gather_variant({"auto": capi.GATHER_AUTO, "ldg": capi.GATHER_LDG, "tma": capi.GATHER_TMA}[args.gather])
+
+    # --- presampling: hotness -> ranking -> interleaved placement (PreSc + CandidateSelection + FillUp) ---
+    scratch = dp.alloc_batch(feature_rows=1)
+    eh = torch.zeros(N, dtype=torch.int64, device=dev)
+    nh = torch.zeros(N, dtype=torch.int64, device=dev)
+    mx = torch.zeros(1, dtype=torch.int32, device=dev)
+    pre = min(args.presample, train_steps)
+    for it in range(pre):
+        dp.run_presc(dp.params(d_train, d_lab, B, it, seed=SEED, batch_id=it), scratch, eh, nh, mx)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.all_reduce(nh)  # init-time 8-way sum of hotness (cache/cache.cu:408-411); not on the serving path
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    order, _ = dp.rank_hotness(nh)
+    kg = world
+    cap = (N + kg - 1) // kg  # whole table cached across the clique
+    dp.build_feature_cache(order, cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
+    max_ids = int(mx.item())
+    feature_rows = min(dp.num_ids, int(max_ids * 1.2) + 1)  # engine/server.cu:277
+    del scratch, eh
+    bufs = [dp.alloc_batch(feature_rows=feature_rows) for _ in range(2)]  # INTERBATCH_CON pipeline slots
+
+    def params(step):
+        return dp.params(d_train, d_lab, B, step % train_steps, seed=SEED, batch_id=step)
+
+    # --- warm-up ---
+    for s in range(args.warmup):
+        dp.run_once(params(s), bufs[s % 2])
+    torch.cuda.synchronize()
+    assert dp.status() == 0, "sampler overflow status"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- timed region: exactly K steps, device-timed, max over ranks ---
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        dp.run_once(params(args.warmup + s), bufs[s % 2], tier=True)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    tiers = dp.tier_rows.clone()
+    if world > 1:
+        dist.all_reduce(tiers)
+    tiers = tiers.cpu().numpy().astype(np.int64)
+    assert dp.status() == 0
+
+    # --- instrumented pass: same steps, CUDA events around each op (per-kernel durations) ---
+    L = dp.L
+    st = dp._stream()
+    names = ["batch_generate", "gather0"] + [x for h in range(1, H + 1) for x in (f"sample{h}", f"gather{h}")]
+    acc = {k: 0.0 for k in names}
+    rows_total = 0
+    n_inst = min(args.steps, 20)
+    for s in range(n_inst):
+        p = params(args.warmup + s)
+        b = bufs[s % 2]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        evs[0].record()
+        capi.check(L.lg_batch_generate(dp.sampler, st, p.all_ids, p.all_labels, p.total_cap, p.batch_size, p.counter,
+                                       C.byref(b.c)))
+        evs[1].record()
+        capi.check(L.lg_feature_cache_lookup(dp.sampler, st, C.byref(dp.cache), 1, dp.local_part, C.byref(b.c), None))
+        evs[2].record()
+        k = 2
+        for hop in range(1, H + 1):
+            capi.check(L.lg_random_sample(dp.sampler, st, C.byref(dp.topo), hop, p.rng_kind, p.rng_seed, p.batch_id,
+                                          p.stream_id, C.byref(b.c), None))
+            k += 1
+            evs[k].record()
+            capi.check(L.lg_feature_cache_lookup(dp.sampler, st, C.byref(dp.cache), 3 * hop + 1, dp.local_part,
+                                                 C.byref(b.c), None))
+            k += 1
+            evs[k].record()
+        torch.cuda.synchronize()
+        for i, nm in enumerate(names):
+            acc[nm] += evs[i].elapsed_time(evs[i + 1])
+        rows_total += int(b.node_counter[9 + H].item())
+    breakdown = {k: v / n_inst for k, v in acc.items()}
+    gather_ms = sum(v for k, v in breakdown.items() if k.startswith("gather"))
+    rows_per_step = rows_total / n_inst
+    alg_bytes = rows_per_step * (8 * D + 8)  # 4D read + 4D written + id + location
+    achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
+    peak, peak_kind = measured_peak()
+
+    # --- end-to-end: host seeds in (pinned), counters out, every step synchronised ---
+    h_ids = torch.from_numpy(my_train[: B * train_steps].copy()).pin_memory()
+    h_lab = lab[torch.from_numpy(my_train[: B * train_steps].astype(np.int64)).to(dev)].cpu().pin_memory()
+    h_nc, h_ec = np.zeros(16, np.int32), np.zeros(16, np.int32)
+
+    def e2e_step(s):
+        c = (args.warmup + s) % train_steps
+        p = params(args.warmup + s)
+        dp.run_once_host(p, h_ids.numpy()[c * B:(c + 1) * B], h_lab.numpy()[c * B:(c + 1) * B], bufs[s % 2], h_nc, h_ec)
+
+    for s in range(min(3, args.warmup)):
+        e2e_step(s)
+    barrier()
+    t_a = time.perf_counter()
+    for s in range(args.steps):
+        e2e_step(s)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t_a
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    # variant with the WHOLE result read back to pinned host memory (not what Legion's trainer does: it reads
+    # the buffers in place over CUDA IPC) — reported for completeness on a few steps
+    n_full = min(5, args.steps)
+    pin = {k: torch.empty_like(getattr(bufs[0], k), device="cpu").pin_memory() for k in ("ids", "agg_src", "agg_dst")}
+    pin_feat = torch.empty((feature_rows, D), dtype=torch.float32).pin_memory()
+    barrier()
+    t_a = time.perf_counter()
+    d2h_full = 0
+    for s in range(n_full):
+        e2e_step(s)
+        n, e = int(h_nc[9 + H]), int(h_ec[9 + H])
+        b = bufs[s % 2]
+        pin["ids"][:n].copy_(b.ids[:n], non_blocking=True)
+        pin["agg_src"][:e].copy_(b.agg_src[:e], non_blocking=True)
+        pin["agg_dst"][:e].copy_(b.agg_dst[:e], non_blocking=True)
+        pin_feat[:n].copy_(b.features[:n], non_blocking=True)
+        torch.cuda.synchronize()
+        d2h_full += 4 * n + 8 * e + 4 * n * D + 128
+    t_full = time.perf_counter() - t_a
+
+    out = None
+    if rank == 0:
+        seeds = world * B * args.steps
+        out = {
+            "metric": "sampled+gathered seeds/sec", "value": seeds / (ms_max * 1e-3), "unit": "seeds/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 ids / fp32 rows moved bit-exact",
+            "data": "synthetic",
+            "config": {"workload": f"{shape['name']}-shaped synthetic graph fully HBM-cached (BASELINE.json configs[1])",
+                       "num_nodes": N, "num_edges": E, "feature_dim": D, "fanout": fanout, "batch": B,
+                       "scale": args.scale, "cache": f"Kc=1,Kg={world}: feature table interleaved by hotness rank over {world} GPU(s); topology replicated in HBM",
+                       "rng": "philox4x32-10", "gather_mover": args.gather,
+                       "l2": "working set (topology + features + per-batch output, >1.5 GB) exceeds the 126 MB L2; every step samples different seeds"},
+            "e2e": {"value": seeds / t_e2e, "unit": "seeds/s", "h2d_bytes_per_step": 2 * 4 * B, "d2h_bytes_per_step": 128,
+                    "note": "host seed ids+labels in pinned memory -> lg_run_batch_host -> both counter arrays read back, "
+                            "stream synchronised every step; features/COO stay in the CUDA-IPC buffers as in Legion's hand-off"},
+            "e2e_host_result": {"value": world * B * n_full / t_full, "unit": "seeds/s", "steps": n_full,
+                                "d2h_bytes_per_step": d2h_full // max(n_full, 1),
+                                "note": "same, plus ids/COO/features copied back to pinned host memory every step"},
+            "gpu_launches": 0,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "feature gather (3 launches per step)",
+                         "algorithmic_bytes_per_step": alg_bytes, "rows_per_step": rows_per_step,
+                         "gather_ms_per_step": gather_ms},
+            "breakdown_ms": breakdown,
+            "tier_rows": {"local": int(tiers[0]), "peer": int(tiers[1]), "host_or_backing": int(tiers[2])},
+            "clocks": clk,
+        }
+        out["gpu_launches"] = args.steps * (1 + (H + 1) + 2 * H)  # batch_generate + gathers + (sample, rank) per hop
+        tr = recorded_traffic()
+        if tr:
+            out["roofline"]["traffic"] = tr.get("traffic_bytes_per_step")
+            out["roofline"]["traffic_source"] = tr.get("source")
+    # --- CPU baseline beside it (rank 0, N=1 only) ---
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_arm(shape, ip.cpu().numpy(), ix.cpu().numpy(), feat.cpu().numpy(), my_train, steps=args.cpu_steps,
+                                      warmup=1)["cpu_baseline"]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the baseline BASELINE.json names): DGL-semantics sampler + index_select
+# ----------------------------------------------------------------------------------------------
+def cpu_arm(shape, indptr, indices, feat, train, steps, warmup):
+    from oracle import oracle as O
+    B, fanout, D = shape["batch"], shape["fanout"], shape["D"]
+    base = O.DGLBaseline(indptr, indices, fanout, B)
+    out = np.empty((O.num_ids(B, fanout), D), np.float32)
+    n_batches = (len(train) - 1) // B
+    times, rows = [], 0
+    for s in range(warmup + steps):
+        seeds = train[(s % n_batches) * B:(s % n_batches + 1) * B]
+        t = time.perf_counter()
+        n = base.sample(seeds, rng_seed=SEED + s)
+        base.gather(feat, n, out)
+        dt = time.perf_counter() - t
+        if s >= warmup:
+            times.append(dt)
+            rows += n
+    tot = sum(times)
+    val = B * steps / tot
+    return {"value": val, "ms_per_step": 1e3 * tot / steps,
+            "cpu_baseline": {"value": val, "unit": "seeds/s", "cores": base.threads(), "kind": "port",
+                             "sample": f"{steps} batches of {B} seeds, fanout {fanout}, DGL-semantics sampler (without replacement, "
+                                       f"unique frontier) + index_select over {rows // max(steps, 1)} rows/batch, OpenMP {base.threads()} threads",
+                             "gather_GBps": rows * (8 * D + 8) / tot / 1e9}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape = shape_of(args)
+    t0 = time.time()
+    indptr = indices = feat = None
+    try:
+        import torch
+        if torch.cuda.is_available():  # data generation only; the timed path below is pure CPU
+            ip, ix, f, _, _ = device_dataset(shape, 0)
+            indptr, indices, feat = ip.cpu().numpy(), ix.cpu().numpy(), f.cpu().numpy()
+            del ip, ix, f
+    except Exception as ex:  # noqa: BLE001
+        log(f"[reference] device generator unavailable ({ex}); using numpy")
+    if indptr is None:
+        from legion_b200 import synth
+        indptr, indices = synth.graph(shape["N"], shape["dmin"], shape["dmax"], SEED)
+        feat = np.concatenate([synth.features(r, min(65536, shape["N"] - r), shape["D"], SEED)
+                               for r in range(0, shape["N"], 65536)])
+    train = train_split(shape, 1)[0]
+    log(f"[reference] dataset ready in {time.time() - t0:.1f}s")
+    r = cpu_arm(shape, indptr, indices, feat, train, steps=args.steps, warmup=args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {"impl": "reference", "metric": "sampled+gathered seeds/sec", "value": r["value"], "unit": "seeds/s",
+           "n_gpus": max(args.gpus, world), "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 ids / fp32 rows", "data": "synthetic",
+           "config": {"workload": f"{shape['name']}-shaped synthetic graph (BASELINE.json configs[0]: CPU sampler + index_select)",
+                      "num_nodes": shape["N"], "num_edges": int(indptr[-1]), "feature_dim": shape["D"],
+                      "fanout": shape["fanout"], "batch": shape["batch"], "scale": args.scale},
+           "cpu_baseline": r["cpu_baseline"],
+           "e2e": {"value": r["value"], "unit": "seeds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="scale N and E of the named shape (1.0 = paper size)")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--presample", type=int, default=20, help="presampling batches used for the hotness ranking")
+    ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 50 and "--steps" not in sys.argv:
+            args.steps = 20
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,117 @@
+"""-m gpu: gather kernels (LDG and TMA movers) bit-exact against the oracle / numpy index_select."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from gpu_util import Rig  # noqa: E402
+from conftest import small_graph  # noqa: E402
+from legion_b200 import capi, synth  # noqa: E402
+
+
+def _gather(rig, ids, variant, tier=None):
+    d_ids = torch.from_numpy(ids).to(rig.dev)
+    out = torch.full((len(ids), rig.D), 777.0, dtype=torch.float32, device=rig.dev)
+    st = rig.dp._stream()
+    capi.check(rig.dp.L.lg_gather_rows(st, C.byref(rig.dp.cache), d_ids.data_ptr(), len(ids), out.data_ptr(), 0, variant,
+                                       tier.data_ptr() if tier is not None else None))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("variant", [capi.GATHER_LDG, capi.GATHER_TMA])
+@pytest.mark.parametrize("dim", [100, 128, 256, 4, 3, 130])
+@pytest.mark.parametrize("host_features", [False, True])
+def test_gather_bit_exact(oracle, variant, dim, host_features):
+    indptr, indices = small_graph(1500, 6.0, 50)
+    N = len(indptr) - 1
+    feat = synth.features(0, N, dim, 77)
+    rig = Rig(indptr, indices, feat, [2], 8, host_features=host_features)
+    rng = np.random.default_rng(dim)
+    hot = torch.from_numpy(rng.integers(0, 1000, N).astype(np.int64)).to(rig.dev)
+    order, _ = rig.dp.rank_hotness(hot)
+    directory = rig.dp.build_feature_cache(order, cap=600)
+    for n in (1, 31, 32, 33, 1000, 4097):
+        ids = rng.integers(0, N, n).astype(np.int32)
+        if n > 40:
+            ids[5] = -1  # skipped row (cache_impl.cuh:263-264): destination untouched
+            ids[37] = -1
+        tier = torch.zeros(3, dtype=torch.int64, device=rig.dev)
+        got = _gather(rig, ids, variant, tier)
+        want = np.full((n, dim), 777.0, np.float32)
+        d = directory.cpu().numpy()
+        shard = rig.dp.feat_shard.tensor(torch.float32, (600, dim)).cpu().numpy()
+        oracle.feature_lookup(ids, 0, n, d, [shard], 600, feat, dim, want)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (n, dim)
+        ok = ids >= 0
+        assert np.array_equal(got[ok].view(np.uint32), feat[ids[ok]].view(np.uint32))
+        t = tier.cpu().numpy()
+        assert t[0] == (d[ids[ok]] >= 0).sum() and t[2] == (d[ids[ok]] < 0).sum() and t[1] == 0
+
+
+@pytest.mark.parametrize("variant", [capi.GATHER_LDG, capi.GATHER_TMA])
+def test_gather_without_cache_reads_backing(variant):
+    indptr, indices = small_graph(800, 6.0, 50)
+    N = len(indptr) - 1
+    feat = synth.features(0, N, 100, 3)
+    rig = Rig(indptr, indices, feat, [2], 8)
+    ids = np.random.default_rng(0).integers(0, N, 5000).astype(np.int32)
+    got = _gather(rig, ids, variant)
+    assert np.array_equal(got.view(np.uint32), feat[ids].view(np.uint32))
+
+
+def test_cache_build_matches_oracle(oracle):
+    indptr, indices = small_graph(2500, 9.0, 120)
+    N = len(indptr) - 1
+    dim = 100
+    feat = synth.features(0, N, dim, 8)
+    rig = Rig(indptr, indices, feat, [2], 8, host_topology=True, host_features=True)
+    rng = np.random.default_rng(4)
+    hot_np = rng.integers(0, 50, N).astype(np.uint64)  # many ties
+    order, sh = rig.dp.rank_hotness(torch.from_numpy(hot_np.astype(np.int64)).to(rig.dev))
+    w_order, w_sh = oracle.hotness_rank(hot_np)
+    assert np.array_equal(order.cpu().numpy(), w_order)
+    L, st = rig.dp.L, rig.dp._stream()
+    for kg, cap in [(1, 300), (4, 200), (8, 313), (8, 400)]:  # last: cap*kg > N -> ranks past N skipped
+        d = torch.empty(N, dtype=torch.int32, device=rig.dev)
+        capi.check(L.lg_fill_i32(st, d.data_ptr(), -2, N))
+        capi.check(L.lg_place_features(st, order.data_ptr(), cap, kg, N, d.data_ptr()))
+        assert np.array_equal(d.cpu().numpy(), oracle.place_features(w_order, cap, kg, N))
+        capi.check(L.lg_fill_i32(st, d.data_ptr(), -2, N))
+        capi.check(L.lg_place_topology(st, order.data_ptr(), cap, kg, 0, N, d.data_ptr()))
+        assert np.array_equal(d.cpu().numpy(), oracle.place_topology(w_order, cap, kg, 0, N))
+        for j in (0, kg - 1):
+            sh_t = torch.empty((cap, dim), dtype=torch.float32, device=rig.dev)
+            capi.check(L.lg_fill_feature_shard(st, order.data_ptr(), cap, kg, j, dim, N, rig.dp._backing, sh_t.data_ptr()))
+            assert np.array_equal(sh_t.cpu().numpy().view(np.uint32),
+                                  oracle.fill_feature_shard(w_order, cap, kg, j, feat).view(np.uint32))
+            sip = torch.empty(cap + 1, dtype=torch.int64, device=rig.dev)
+            capi.check(L.lg_topo_shard_indptr(st, order.data_ptr(), cap, kg, j, N, rig.dp._full[0], sip.data_ptr()))
+            w_sip, w_six = oracle.fill_topo_shard(w_order, cap, kg, j, indptr, indices)
+            assert np.array_equal(sip.cpu().numpy(), w_sip)
+            six = torch.empty(max(int(w_sip[-1]), 1), dtype=torch.int32, device=rig.dev)
+            capi.check(L.lg_topo_shard_fill(st, order.data_ptr(), cap, kg, j, N, rig.dp._full[0], rig.dp._full[1],
+                                            sip.data_ptr(), six.data_ptr()))
+            assert np.array_equal(six.cpu().numpy()[: int(w_sip[-1])], w_six)
+
+
+def test_synth_device_generator_matches_numpy():
+    L = capi.load()
+    N, dmin, dmax, seed = 30000, 5.25, 700, 0x1e910
+    ip = torch.empty(N + 1, dtype=torch.int64, device="cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.check(L.lg_synth_indptr(st, N, dmin, dmax, seed, ip.data_ptr()))
+    w_ip, w_ix = synth.graph(N, dmin, dmax, seed)
+    assert np.array_equal(ip.cpu().numpy(), w_ip)
+    ix = torch.empty(int(w_ip[-1]), dtype=torch.int32, device="cuda:0")
+    capi.check(L.lg_synth_indices(st, N, ip.data_ptr(), seed, ix.data_ptr()))
+    assert np.array_equal(ix.cpu().numpy(), w_ix)
+    f = torch.empty((500, 100), dtype=torch.float32, device="cuda:0")
+    capi.check(L.lg_synth_features(st, 1234, 500, 100, seed, f.data_ptr()))
+    assert np.array_equal(f.cpu().numpy().view(np.uint32), synth.features(1234, 500, 100, seed).view(np.uint32))
+    lab = torch.empty(N, dtype=torch.int32, device="cuda:0")
+    capi.check(L.lg_synth_labels(st, N, 47, lab.data_ptr()))
+    assert np.array_equal(lab.cpu().numpy(), synth.labels(N, 47))

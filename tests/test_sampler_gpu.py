@@ -1,0 +1,245 @@
+"""-m gpu: the CUDA sampler (through the C ABI) against the CPU oracle, bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from conftest import make_sets, small_graph  # noqa: E402
+from gpu_util import Rig, assert_batch_equal  # noqa: E402
+from legion_b200 import capi, synth  # noqa: E402
+
+
+def _feat(n, d=8):
+    return synth.features(0, n, d, 5)
+
+
+@pytest.mark.parametrize("rng", [capi.RNG_MINSTD, capi.RNG_PHILOX])
+@pytest.mark.parametrize("fanout,batch", [([5, 3], 64), ([25, 10], 256), ([15, 10, 5], 100), ([3], 17), ([40, 2], 33)])
+def test_batch_matches_oracle(oracle, rng, fanout, batch):
+    indptr, indices = small_graph(3000, 14.0, 400)
+    N = len(indptr) - 1
+    feat = _feat(N)
+    ids, labels = make_sets(N)
+    rig = Rig(indptr, indices, feat, fanout, batch)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    orc = oracle.Oracle(indptr, indices, fanout, batch)
+    for counter in (0, 3):
+        p = rig.dp.params(d_ids, d_lab, batch, counter, rng_kind=rng, seed=0xABCDEF0123, batch_id=counter, stream_id=2)
+        rig.dp.run_once(p, buf)
+        torch.cuda.synchronize()
+        want = orc.run_batch(ids, labels, batch, counter, rng_kind=rng, seed=0xABCDEF0123, batch_id=counter, stream_id=2)
+        assert_batch_equal(buf.to_host(len(fanout)), want, len(fanout), feat)
+    assert rig.dp.status() == 0
+
+
+def test_per_op_counter_trace(oracle):
+    """counters after every op equal the reference state machine (engine/operator_impl.cu:57-89)"""
+    indptr, indices = small_graph()
+    N = len(indptr) - 1
+    ids, labels = make_sets(N)
+    fanout, B = [6, 4], 50
+    rig = Rig(indptr, indices, _feat(N), fanout, B)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    L, dp = rig.dp.L, rig.dp
+    st = dp._stream()
+    want = oracle.Oracle(indptr, indices, fanout, B).run_batch(ids, labels, B, 1, seed=5, batch_id=1, per_hop=True)
+    trace = {op: (nc, ec) for op, nc, ec in want["trace"]}
+
+    def snap():
+        torch.cuda.synchronize()
+        return buf.node_counter.cpu().numpy(), buf.edge_counter.cpu().numpy()
+
+    capi.check(L.lg_batch_generate(dp.sampler, st, d_ids.data_ptr(), d_lab.data_ptr(), len(ids), B, 1, C.byref(buf.c)))
+    nc, ec = snap()
+    assert np.array_equal(nc, trace[0][0]) and np.array_equal(ec, trace[0][1])
+    capi.check(L.lg_feature_cache_lookup(dp.sampler, st, C.byref(dp.cache), 1, 0, C.byref(buf.c), None))
+    nc, ec = snap()
+    assert np.array_equal(nc, trace[1][0]) and np.array_equal(ec, trace[1][1])
+    for hop in (1, 2):
+        capi.check(L.lg_random_sample(dp.sampler, st, C.byref(dp.topo), hop, capi.RNG_PHILOX, 5, 1, 0, C.byref(buf.c), None))
+        nc, ec = snap()
+        assert np.array_equal(nc, trace[3 * hop][0]) and np.array_equal(ec, trace[3 * hop][1]), hop
+        capi.check(L.lg_feature_cache_lookup(dp.sampler, st, C.byref(dp.cache), 3 * hop + 1, 0, C.byref(buf.c), None))
+        nc, ec = snap()
+        assert np.array_equal(nc, trace[3 * hop + 1][0]) and np.array_equal(ec, trace[3 * hop + 1][1]), hop
+
+
+def test_edge_cases(oracle):
+    # isolated vertices (deg 0), deg < fanout, duplicate seeds, -1 padded tail, empty batch
+    rng = np.random.default_rng(11)
+    N = 400
+    deg = rng.integers(0, 9, N)
+    deg[::5] = 0
+    indptr = np.zeros(N + 1, np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = rng.integers(0, N, int(indptr[-1])).astype(np.int32)
+    feat = _feat(N)
+    fanout, B = [4, 3], 40
+    ids = rng.permutation(N).astype(np.int32)[:130]
+    ids[5] = ids[3]  # duplicate seed: first position wins in oracle and kernel
+    labels = (ids % 3).astype(np.int32)
+    rig = Rig(indptr, indices, feat, fanout, B)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    orc = oracle.Oracle(indptr, indices, fanout, B)
+    for counter in (0, 1, 2, 3, 4):  # 3 = clipped tail (130 - 120 = 10 seeds), 4 = empty
+        buf.features.fill_(777.0)
+        p = rig.dp.params(d_ids, d_lab, B, counter, seed=1, batch_id=counter)
+        rig.dp.run_once(p, buf)
+        torch.cuda.synchronize()
+        want = orc.run_batch(ids, labels, B, counter, seed=1, batch_id=counter)
+        assert_batch_equal(buf.to_host(2), want, 2, feat)
+    assert want["total_nodes"] == 0 and want["total_edges"] == 0
+
+
+def test_tail_padding_minus_one(oracle):
+    """ids past total_cap become -1 and produce nothing (engine/operator_impl.cu:40-42,218); reached through
+    the kernel-level rule size*counter+idx >= total_cap"""
+    indptr, indices = small_graph(500, 8.0, 60)
+    N = len(indptr) - 1
+    ids, labels = make_sets(N, 0.2)  # 100 ids
+    rig = Rig(indptr, indices, _feat(N), [3, 2], 64)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    orc = oracle.Oracle(indptr, indices, [3, 2], 64)
+    p = rig.dp.params(d_ids, d_lab, 64, 1, seed=3, batch_id=1)  # clipped: size = 36, stride 36 (reference quirk)
+    rig.dp.run_once(p, buf)
+    torch.cuda.synchronize()
+    want = orc.run_batch(ids, labels, 64, 1, seed=3, batch_id=1)
+    assert want["nc"][9] == 36
+    assert_batch_equal(buf.to_host(2), want, 2)
+
+
+def test_small_table_forces_collisions(oracle):
+    indptr, indices = small_graph(3000, 14.0, 400)
+    N = len(indptr) - 1
+    ids, labels = make_sets(N)
+    fanout, B = [10, 5], 128
+    rig = Rig(indptr, indices, _feat(N), fanout, B)
+    slots = 1
+    while slots <= rig.dp.num_ids:
+        slots *= 2
+    capi.check(rig.dp.L.lg_sampler_set_table_slots(rig.dp.sampler, slots))  # load factor up to ~1
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    p = rig.dp.params(d_ids, d_lab, B, 2, seed=9, batch_id=2)
+    rig.dp.run_once(p, buf)
+    torch.cuda.synchronize()
+    want = oracle.Oracle(indptr, indices, fanout, B).run_batch(ids, labels, B, 2, seed=9, batch_id=2)
+    assert_batch_equal(buf.to_host(2), want, 2)
+    assert rig.dp.L.lg_sampler_set_table_slots(rig.dp.sampler, 1024) != 0  # too small: refused
+
+
+@pytest.mark.parametrize("host_topology", [False, True])
+def test_topology_cache_tiers_do_not_change_the_sample(oracle, host_topology):
+    """hot rows from an HBM shard, the rest from the full CSR (HBM or host UVA): identical output
+    (engine/operator_impl.cu:224-243)"""
+    indptr, indices = small_graph(3000, 14.0, 400)
+    N = len(indptr) - 1
+    feat = _feat(N)
+    ids, labels = make_sets(N)
+    fanout, B = [8, 4], 100
+    rig = Rig(indptr, indices, feat, fanout, B, host_topology=host_topology, host_features=host_topology)
+    hot = torch.from_numpy(np.bincount(indices, minlength=N).astype(np.int64)).to(rig.dev)
+    order, _ = rig.dp.rank_hotness(hot)
+    rig.dp.build_topology_cache(order, cap=700)
+    rig.dp.build_feature_cache(order, cap=500)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    p = rig.dp.params(d_ids, d_lab, B, 1, seed=4, batch_id=1)
+    rig.dp.run_once(p, buf, tier=True)
+    torch.cuda.synchronize()
+    want = oracle.Oracle(indptr, indices, fanout, B).run_batch(ids, labels, B, 1, seed=4, batch_id=1)
+    assert_batch_equal(buf.to_host(2), want, 2, feat)
+    tiers = rig.dp.tier_rows.cpu().numpy()
+    assert tiers.sum() == want["total_nodes"] and tiers[0] > 0 and tiers[2] > 0 and tiers[1] == 0
+
+
+def test_presampling_hotness(oracle):
+    """pre_sample edge counts + HotnessMeasure + max ids (operator_impl.cu:358; cache_impl.cuh:190-198; cache.cu:59-61)"""
+    indptr, indices = small_graph()
+    N = len(indptr) - 1
+    ids, labels = make_sets(N)
+    fanout, B = [5, 3], 64
+    rig = Rig(indptr, indices, _feat(N), fanout, B, host_topology=True)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch(feature_rows=1)
+    eh = torch.zeros(N, dtype=torch.int64, device=rig.dev)
+    nh = torch.zeros(N, dtype=torch.int64, device=rig.dev)
+    mx = torch.zeros(1, dtype=torch.int32, device=rig.dev)
+    w_eh, w_nh, w_mx = np.zeros(N, np.uint64), np.zeros(N, np.uint64), 0
+    orc = oracle.Oracle(indptr, indices, fanout, B)
+    for it in range(6):
+        p = rig.dp.params(d_ids, d_lab, B, it, seed=2, batch_id=it)
+        rig.dp.run_presc(p, buf, eh, nh, mx)
+        o = orc.run_batch(ids, labels, B, it, seed=2, batch_id=it, edge_hot=w_eh, node_hot=w_nh)
+        w_mx = max(w_mx, o["max_ids"])
+    torch.cuda.synchronize()
+    assert np.array_equal(eh.cpu().numpy().astype(np.uint64), w_eh)
+    assert np.array_equal(nh.cpu().numpy().astype(np.uint64), w_nh)
+    assert int(mx.item()) == w_mx
+    # ranking parity (ties by ascending id)
+    order, sh = rig.dp.rank_hotness(nh)
+    w_order, w_sh = oracle.hotness_rank(w_nh)
+    assert np.array_equal(order.cpu().numpy(), w_order) and np.array_equal(sh.cpu().numpy().astype(np.uint64), w_sh)
+
+
+def test_e2e_host_call_matches_device_call(oracle):
+    indptr, indices = small_graph()
+    N = len(indptr) - 1
+    feat = _feat(N)
+    ids, labels = make_sets(N)
+    fanout, B = [5, 3], 64
+    rig = Rig(indptr, indices, feat, fanout, B)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    h_ids = torch.from_numpy(ids[128:192].copy()).pin_memory()
+    h_lab = torch.from_numpy(labels[128:192].copy()).pin_memory()
+    nc, ec = np.zeros(16, np.int32), np.zeros(16, np.int32)
+    p = rig.dp.params(d_ids, d_lab, B, 2, seed=6, batch_id=2)
+    rig.dp.run_once_host(p, h_ids.numpy(), h_lab.numpy(), buf, nc, ec)
+    want = oracle.Oracle(indptr, indices, fanout, B).run_batch(ids, labels, B, 2, seed=6, batch_id=2)
+    assert np.array_equal(nc, want["nc"]) and np.array_equal(ec, want["ec"])
+    assert_batch_equal(buf.to_host(2), want, 2, feat)
+
+
+def test_distribution_fanout_and_uniformity(oracle):
+    """fan-out bound and per-draw uniformity (chi-square) of the with-replacement pick; inclusion frequency
+    against the DGL-semantics sampler's c/deg (without replacement) where the two are comparable"""
+    N, degv, c = 64, 40, 10
+    indptr = np.arange(N + 1, dtype=np.int64) * degv
+    indices = np.tile(np.arange(degv, dtype=np.int32), N)  # vertex v's neighbours are 0..39
+    feat = _feat(N)
+    seeds = np.arange(N, dtype=np.int32)
+    rig = Rig(indptr, indices, feat, [c], N)
+    d_ids, d_lab = rig.sets(seeds, seeds)
+    buf = rig.dp.alloc_batch()
+    counts = np.zeros(degv, np.int64)
+    n_batches = 200
+    for b in range(n_batches):
+        p = rig.dp.params(d_ids, d_lab, N, 0, seed=0x5EED, batch_id=b)
+        rig.dp.run_once(p, buf, gather=False)
+        torch.cuda.synchronize()
+        h = buf.to_host(1)
+        assert h["total_edges"] == N * c  # min(deg, fanout) draws per seed
+        per_dst = np.bincount(h["agg_dst"], minlength=N)
+        assert (per_dst == c).all()
+        counts += np.bincount(h["ids"][h["agg_src"]], minlength=degv)
+    total = counts.sum()
+    chi2 = ((counts - total / degv) ** 2 / (total / degv)).sum()
+    assert chi2 < 80.0, chi2  # 39 dof: p(chi2 > 80) ~ 1e-4
+    # DGL-like baseline: inclusion probability c/deg per neighbour; ours 1-(1-1/deg)^c per seed
+    base = oracle.DGLBaseline(indptr, indices, [c], N)
+    inc_dgl = np.zeros(degv)
+    for b in range(50):
+        base.sample(seeds, rng_seed=b + 1)
+        e = int(base.le[1])
+        assert e == N * c
+        inc_dgl += np.bincount(base.ids[base.src[:e]], minlength=degv)
+    inc_dgl /= 50 * N
+    assert abs(inc_dgl.mean() - c / degv) < 1e-9 and np.abs(inc_dgl - c / degv).max() < 0.05
