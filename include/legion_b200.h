@@ -252,6 +252,17 @@ int lg_stream_destroy(lg_stream_t stream);
 int lg_stream_synchronize(lg_stream_t stream);
 int lg_memcpy_h2d(void* dst, const void* src, int64_t bytes, lg_stream_t stream);
 int lg_memcpy_d2h(void* dst, const void* src, int64_t bytes, lg_stream_t stream);
+int lg_memcpy_d2d(void* dst, const void* src, int64_t bytes, lg_stream_t stream);
+int lg_memset_async(void* dst, int32_t byte_value, int64_t bytes, lg_stream_t stream);
+/* events: the op DAG of GPURunner (engine/server.cu:250-260,311-324) */
+typedef void* lg_event_t;
+int lg_event_create(lg_event_t* ev);
+int lg_event_destroy(lg_event_t ev);
+int lg_event_record(lg_event_t ev, lg_stream_t stream);
+int lg_event_query(lg_event_t ev, int32_t* ready); /* ready = 1 when complete */
+int lg_event_synchronize(lg_event_t ev);
+int lg_stream_wait_event(lg_stream_t stream, lg_event_t ev);
+int lg_device_mem_info(int64_t* free_bytes, int64_t* total_bytes);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,15 @@ _PROTOS = {
     "lg_stream_synchronize": (C.c_int, [vp]),
     "lg_memcpy_h2d": (C.c_int, [vp, vp, C.c_int64, vp]),
     "lg_memcpy_d2h": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "lg_memcpy_d2d": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "lg_memset_async": (C.c_int, [vp, C.c_int32, C.c_int64, vp]),
+    "lg_event_create": (C.c_int, [C.POINTER(vp)]),
+    "lg_event_destroy": (C.c_int, [vp]),
+    "lg_event_record": (C.c_int, [vp, vp]),
+    "lg_event_query": (C.c_int, [vp, C.POINTER(C.c_int32)]),
+    "lg_event_synchronize": (C.c_int, [vp]),
+    "lg_stream_wait_event": (C.c_int, [vp, vp]),
+    "lg_device_mem_info": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     # include/legion_b200_synth.h
     "lg_synth_indptr": (C.c_int, [vp, C.c_int64, C.c_double, C.c_int32, C.c_uint64, vp]),
     "lg_synth_indices": (C.c_int, [vp, C.c_int64, vp, C.c_uint64, vp]),

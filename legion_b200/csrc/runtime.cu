@@ -112,3 +112,52 @@ extern "C" int lg_memcpy_d2h(void* dst, const void* src, int64_t bytes, lg_strea
   LG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return 0;
 }
+extern "C" int lg_memcpy_d2d(void* dst, const void* src, int64_t bytes, lg_stream_t stream) {
+  LG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lg_memset_async(void* dst, int32_t byte_value, int64_t bytes, lg_stream_t stream) {
+  LG_CUDA(cudaMemsetAsync(dst, byte_value, (size_t)bytes, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lg_event_create(lg_event_t* ev) {
+  LG_REQUIRE(ev, "null");
+  cudaEvent_t e;
+  LG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *ev = (lg_event_t)e;
+  return 0;
+}
+extern "C" int lg_event_destroy(lg_event_t ev) {
+  LG_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+extern "C" int lg_event_record(lg_event_t ev, lg_stream_t stream) {
+  LG_CUDA(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lg_event_query(lg_event_t ev, int32_t* ready) {
+  LG_REQUIRE(ready, "null");
+  cudaError_t e = cudaEventQuery((cudaEvent_t)ev);
+  if (e == cudaErrorNotReady) {
+    *ready = 0;
+    return 0;
+  }
+  LG_CUDA(e);
+  *ready = 1;
+  return 0;
+}
+extern "C" int lg_event_synchronize(lg_event_t ev) {
+  LG_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
+  return 0;
+}
+extern "C" int lg_stream_wait_event(lg_stream_t stream, lg_event_t ev) {
+  LG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
+  return 0;
+}
+extern "C" int lg_device_mem_info(int64_t* free_bytes, int64_t* total_bytes) {
+  size_t f = 0, t = 0;
+  LG_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return 0;
+}
