@@ -115,6 +115,9 @@ int lg_sampler_set_table_slots(lg_sampler* s, int64_t slots);
 int64_t lg_sampler_scratch_bytes(const lg_sampler* s);
 /* data mover used by lg_feature_cache_lookup: LG_GATHER_AUTO / LG_GATHER_LDG / LG_GATHER_TMA */
 int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant);
+/* lg_run_batch runs the gathers on an internal side stream so that they overlap the sampling of
+ * the next hop (default on); 0 = strictly one stream */
+int lg_sampler_set_overlap(lg_sampler* s, int32_t on);
 /* sticky overflow status (0 ok, 1 ids overflow, 2 features buffer too small — the reference
  * sizes it 1.2 x presampled max without a bound check, engine/server.cu:277).  Synchronises. */
 int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);

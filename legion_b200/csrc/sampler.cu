@@ -435,6 +435,10 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_CUDA(cudaMalloc(&s->status, sizeof(int32_t)));
   LG_CUDA(cudaMemset(s->status, 0, sizeof(int32_t)));
   LG_CUDA(cudaMallocHost(&s->pinned_seeds, (size_t)max_batch * 2 * sizeof(int32_t)));
+  LG_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+  for (int h = 0; h <= LG_MAX_HOPS; h++) LG_CUDA(cudaEventCreateWithFlags(&s->ev_fork[h], cudaEventDisableTiming));
+  LG_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  s->overlap = 1;
   int rc = sampler_alloc_table(s, next_pow2(s->num_ids + s->num_ids / 2));
   if (rc) return rc;
   *out = s;
@@ -450,6 +454,9 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaFree(s->small);
   cudaFree(s->status);
   cudaFreeHost(s->pinned_seeds);
+  cudaStreamDestroy(s->side);
+  for (int h = 0; h <= LG_MAX_HOPS; h++) cudaEventDestroy(s->ev_fork[h]);
+  cudaEventDestroy(s->ev_join);
   delete s;
   return 0;
 }
@@ -467,6 +474,12 @@ extern "C" int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant) {
   LG_REQUIRE(s, "null sampler");
   LG_REQUIRE(variant >= LG_GATHER_AUTO && variant <= LG_GATHER_TMA, "gather variant %d", variant);
   s->gather_variant = variant;
+  return 0;
+}
+
+extern "C" int lg_sampler_set_overlap(lg_sampler* s, int32_t on) {
+  LG_REQUIRE(s, "null sampler");
+  s->overlap = on ? 1 : 0;
   return 0;
 }
 
@@ -586,15 +599,33 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
                             const lg_feature_cache* cache, const lg_batch_params* p, const lg_batch* b,
                             unsigned long long* tier_rows) {
   LG_REQUIRE(s && topo && p && b, "lg_run_batch: null argument");
+  cudaStream_t main_st = (cudaStream_t)stream;
+  const bool fork = cache && s->overlap;
+  // gathers go to the side stream (HBM-bound) while the next hop is sampled on the caller's stream
+  // (latency-bound): both kinds of kernels are resident on the SMs at once.
+  lg_stream_t gst = fork ? (lg_stream_t)s->side : stream;
+  if (fork) {  // the side stream must not start before the caller's earlier work (previous batch) is done
+    LG_CUDA(cudaEventRecord(s->ev_join, main_st));
+    LG_CUDA(cudaStreamWaitEvent(s->side, s->ev_join, 0));
+  }
   int rc = lg_batch_generate(s, stream, p->all_ids, p->all_labels, p->total_cap, p->batch_size, p->counter, b);
   if (rc) return rc;
-  if (cache && (rc = lg_feature_cache_lookup(s, stream, cache, 1, p->local_part, b, tier_rows))) return rc;
-  for (int hop = 1; hop <= s->n_hops; hop++) {
-    rc = lg_random_sample(s, stream, topo, hop, p->rng_kind, p->rng_seed, p->batch_id, p->stream_id, b, nullptr);
+  for (int hop = 0; hop <= s->n_hops; hop++) {
+    if (hop > 0) {
+      rc = lg_random_sample(s, stream, topo, hop, p->rng_kind, p->rng_seed, p->batch_id, p->stream_id, b, nullptr);
+      if (rc) return rc;
+    }
+    if (!cache) continue;
+    if (fork) {
+      LG_CUDA(cudaEventRecord(s->ev_fork[hop], main_st));
+      LG_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork[hop], 0));
+    }
+    rc = lg_feature_cache_lookup(s, gst, cache, hop * LG_INTRABATCH_CON + 1, p->local_part, b, tier_rows);
     if (rc) return rc;
-    if (cache && (rc = lg_feature_cache_lookup(s, stream, cache, hop * LG_INTRABATCH_CON + 1, p->local_part, b,
-                                               tier_rows)))
-      return rc;
+  }
+  if (fork) {  // join: the batch is complete on the caller's stream
+    LG_CUDA(cudaEventRecord(s->ev_join, s->side));
+    LG_CUDA(cudaStreamWaitEvent(main_st, s->ev_join, 0));
   }
   return lg_io_complete(s, stream, p->mode, b, nullptr, nullptr);
 }

@@ -30,4 +30,10 @@ struct lg_sampler {
   int32_t rank_tiles[LG_MAX_HOPS];
   int32_t* status;       // device int32: 1 = ids overflow, 2 = features buffer overflow
   int32_t* pinned_seeds;
+  // gather/sampling overlap inside lg_run_batch: the gather of hop h runs on `side` while hop h+1
+  // is sampled on the caller's stream (the reference's stream-1 / stream-0 split, server.cu:311-317)
+  cudaStream_t side;
+  cudaEvent_t ev_fork[LG_MAX_HOPS + 1];
+  cudaEvent_t ev_join;
+  int32_t overlap;
 };

@@ -330,5 +330,8 @@ class DataPath:
         check(self.L.lg_sampler_status(self.sampler, self._stream(), C.byref(s)))
         return s.value
 
+    def set_overlap(self, on):
+        check(self.L.lg_sampler_set_overlap(self.sampler, 1 if on else 0))
+
     def set_gather_variant(self, v):
         check(self.L.lg_sampler_set_gather_variant(self.sampler, v))

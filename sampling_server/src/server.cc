@@ -1,0 +1,258 @@
+// server.cc — GPUServer / GPURunner (reference: engine/server.cu:44-370).
+// One host thread per GPU; per GPU three streams and an op DAG of (hops+1)*3+1 operators.  The
+// gather of hop h (stream 1) overlaps the sampling of hop h+1 (stream 0) exactly as in the
+// reference; unlike the reference (which polls only the last op's event, server.cu:319-324, and
+// can post a batch whose gather is still running) every stream is joined before IPCPost.
+#include "server.h"
+
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <thread>
+
+#include "cache.h"
+#include "ipc_service.h"
+#include "memorypool.h"
+#include "operator.h"
+#include "storage.h"
+
+namespace {
+void PreSCLoop(int train_step, Runner* runner, RunnerParams* params) {
+  for (int i = 0; i < train_step; i++) {
+    params->global_batch_id = i;
+    runner->RunPreSc(params);
+  }
+  runner->InitializeFeaturesBuffer(params);
+}
+void RunnerLoop(int max_step, Runner* runner, RunnerParams* params) {
+  for (int i = 0; i < max_step; i++) {
+    params->global_batch_id = i;
+    runner->RunOnce(params);
+  }
+}
+
+class GPUServer : public Server {
+ public:
+  void Initialize(int global_shard_count, std::vector<int> fanout, int in_memory_mode) override {
+    shard_count_ = global_shard_count;
+    std::cout << (in_memory_mode ? "In Memory Mode\n" : "In Disk Mode\n");
+    storage_ = new StorageManagement();
+    storage_->Initialze(shard_count_, in_memory_mode, fanout);
+    if (!storage_->GetInfo()->fanout.empty()) fanout = storage_->GetInfo()->fanout;  // meta_config extension
+    graph_ = storage_->GetGraph();
+    feature_ = storage_->GetFeature();
+    cache_ = storage_->GetCache();
+    ipc_env_ = storage_->GetIPCEnv();
+    train_step_ = ipc_env_->GetTrainStep();
+    max_step_ = ipc_env_->GetMaxStep();
+    runners_.resize(shard_count_);
+    params_.resize(shard_count_);
+    for (int i = 0; i < shard_count_; i++) {
+      LGCHECK(lg_set_device(i));
+      auto* p = new RunnerParams();
+      p->device_id = i;
+      p->fanout = fanout;
+      p->cache = cache_;
+      p->graph = graph_;
+      p->feature = feature_;
+      p->env = ipc_env_;
+      p->global_batch_id = 0;
+      p->in_memory = true;
+      params_[i] = p;
+      runners_[i] = NewGPURunner();
+      runners_[i]->Initialize(p);
+    }
+  }
+
+  void PreSc(int cache_agg_mode) override {
+    auto t1 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int i = 0; i < shard_count_; i++) pool.emplace_back(&PreSCLoop, train_step_, runners_[i], params_[i]);
+    for (auto& th : pool) th.join();
+    std::vector<uint64_t> counters(2, 0);  // PCM PCIe counters: disabled in the reference (server.cu:106)
+    double t = std::chrono::duration_cast<std::chrono::duration<double>>(std::chrono::steady_clock::now() - t1).count();
+    cache_->CandidateSelection(cache_agg_mode, feature_, graph_);
+    cache_->CostModel(cache_agg_mode, feature_, graph_, counters, train_step_);
+    cache_->FillUp(cache_agg_mode, feature_, graph_);
+    std::cout << "Preprocessing cost: " << t << " s\n";
+    std::cout << "System is ready for serving\n" << std::flush;
+  }
+
+  void Run() override {
+    std::vector<std::thread> pool;
+    for (int i = 0; i < shard_count_; i++) pool.emplace_back(&RunnerLoop, max_step_, runners_[i], params_[i]);
+    for (auto& th : pool) th.join();
+  }
+
+  void Finalize() override {
+    for (int i = 0; i < shard_count_; i++) runners_[i]->Finalize(params_[i]);
+    graph_->Finalize();
+    feature_->Finalize();
+    ipc_env_->Finalize();
+    std::cout << "Server Stopped\n" << std::flush;
+  }
+
+ private:
+  StorageManagement* storage_ = nullptr;
+  GraphStorage* graph_ = nullptr;
+  FeatureStorage* feature_ = nullptr;
+  UnifiedCache* cache_ = nullptr;
+  IPCEnv* ipc_env_ = nullptr;
+  int shard_count_ = 0, train_step_ = 0, max_step_ = 0;
+  std::vector<Runner*> runners_;
+  std::vector<RunnerParams*> params_;
+};
+
+class GPURunner : public Runner {
+ public:
+  void Initialize(RunnerParams* params) override {
+    LGCHECK(lg_set_device(params->device_id));
+    local_dev_id_ = params->device_id;
+    auto* cache = (UnifiedCache*)params->cache;
+    auto* feature = (FeatureStorage*)params->feature;
+    auto* env = (IPCEnv*)params->env;
+    streams_.resize(INTRABATCH_CON);
+    for (auto& s : streams_) LGCHECK(lg_stream_create(&s));
+    int batch_size = env->GetRawBatchsize();
+    int hop_num = (int)params->fanout.size();
+    num_ids_ = (int32_t)lg_num_ids(batch_size, params->fanout.data(), hop_num);  // server.cu:187-199
+    op_num_ = (hop_num + 1) * INTRABATCH_CON + 1;
+    ops_.resize(op_num_);
+    ops_[0] = NewBatchGenerateOP(0);
+    ops_[1] = NewCacheLookupOP(1);
+    ops_[2] = NewSSDIOSubmitOP(2);
+    for (int i = 0; i < hop_num; i++) {
+      ops_[INTRABATCH_CON * i + 3] = NewRandomSampleOP(INTRABATCH_CON * i + 3);
+      ops_[INTRABATCH_CON * i + 4] = NewCacheLookupOP(INTRABATCH_CON * i + 4);
+      ops_[INTRABATCH_CON * i + 5] = NewSSDIOSubmitOP(INTRABATCH_CON * i + 5);
+    }
+    ops_[op_num_ - 1] = NewSSDIOCompleteOP(op_num_ - 1);
+    interbatch_concurrency_ = INTERBATCH_CON;
+    cache->InitializeCacheController(local_dev_id_, feature->TotalNodeNum());
+    memorypool_ = new MemoryPool(interbatch_concurrency_);
+    // valid/test batches can be larger than the raw batch only if their sets are (512-sized steps): take the max
+    int max_batch = batch_size;
+    for (int m : {VALIDMODE, TESTMODE})
+      if (env->GetCurrentBatchsize(local_dev_id_, m) > max_batch) max_batch = env->GetCurrentBatchsize(local_dev_id_, m);
+    LGCHECK(lg_sampler_create(local_dev_id_, max_batch, params->fanout.data(), hop_num, &memorypool_->sampler));
+    if (max_batch > batch_size) num_ids_ = (int32_t)lg_num_ids(max_batch, params->fanout.data(), hop_num);
+    if (const char* e = std::getenv("LEGION_RNG")) memorypool_->rng_kind = std::strcmp(e, "minstd") == 0 ? LG_RNG_MINSTD : LG_RNG_PHILOX;
+    if (const char* e = std::getenv("LEGION_SEED")) memorypool_->rng_seed = std::strtoull(e, nullptr, 0);
+    if (const char* e = std::getenv("LEGION_GATHER")) LGCHECK(lg_sampler_set_gather_variant(memorypool_->sampler, std::atoi(e)));
+    float_feature_len_ = feature->GetFloatFeatureLen();
+    max_batch_ = max_batch;
+    env->InitializeSamplesBuffer(max_batch, num_ids_, float_feature_len_, local_dev_id_, interbatch_concurrency_);
+    current_pipe_ = 0;
+    for (int i = 0; i < interbatch_concurrency_; i++) {
+      lg_batch* b = memorypool_->Batch(i);
+      std::memset(b, 0, sizeof(*b));
+      b->ids = env->GetIds(local_dev_id_, i);
+      b->labels = env->GetLabels(local_dev_id_, i);
+      b->agg_src = env->GetAggSrc(local_dev_id_, i);
+      b->agg_dst = env->GetAggDst(local_dev_id_, i);
+      b->node_counter = env->GetNodeCounter(local_dev_id_, i);
+      b->edge_counter = env->GetEdgeCounter(local_dev_id_, i);
+      b->num_ids = num_ids_;
+      b->feature_rows = 0;
+    }
+    events_.resize(op_num_);
+    op_params_.resize(op_num_);
+    for (int i = 0; i < op_num_; i++) {
+      auto* op = new OpParams();
+      op->device_id = local_dev_id_;
+      op->stream = streams_[i % INTRABATCH_CON];
+      LGCHECK(lg_event_create(&events_[i]));
+      op->event = events_[i];
+      op->memorypool = memorypool_;
+      op->cache = cache;
+      op->graph = params->graph;
+      op->feature = feature;
+      op->env = env;
+      op->in_memory = params->in_memory;
+      op->hop_num = hop_num;
+      op->neighbor_count = 0;
+      op->is_presc = false;
+      op_params_[i] = op;
+    }
+    for (int i = 0; i < hop_num; i++) op_params_[INTRABATCH_CON * i + INTRABATCH_CON]->neighbor_count = params->fanout[i];
+  }
+
+  void InitializeFeaturesBuffer(RunnerParams* params) override {
+    auto* cache = (UnifiedCache*)params->cache;
+    auto* env = (IPCEnv*)params->env;
+    LGCHECK(lg_set_device(local_dev_id_));
+    int64_t rows = (int64_t)(cache->MaxIdNum(local_dev_id_) * 1.2);  // server.cu:277
+    if (max_batch_ > env->GetRawBatchsize())  // eval batches may be larger than anything presampling saw
+      rows = rows * max_batch_ / env->GetRawBatchsize() + 1;
+    if (rows > num_ids_) rows = num_ids_;
+    if (rows < 1) rows = 1;
+    env->InitializeFeaturesBuffer(0, (int32_t)rows, float_feature_len_, local_dev_id_, interbatch_concurrency_);
+    for (int i = 0; i < interbatch_concurrency_; i++) {
+      memorypool_->Batch(i)->features = env->GetFloatFeatures(local_dev_id_, i);
+      memorypool_->Batch(i)->feature_rows = rows;
+    }
+  }
+
+  void RunPreSc(RunnerParams* params) override {
+    LGCHECK(lg_set_device(local_dev_id_));
+    memorypool_->SetCurrentMode(TRAINMODE);
+    memorypool_->SetIter(params->global_batch_id);
+    memorypool_->SetGlobalBatchId(params->global_batch_id);
+    for (int i = 0; i < op_num_; i += INTRABATCH_CON) {  // ops 0,3,6,..: all on stream 0
+      op_params_[i]->is_presc = true;
+      ops_[i]->run(op_params_[i]);
+    }
+    LGCHECK(lg_event_synchronize(op_params_[op_num_ - 1]->event));
+  }
+
+  void RunOnce(RunnerParams* params) override {
+    LGCHECK(lg_set_device(local_dev_id_));
+    auto* env = (IPCEnv*)params->env;
+    int32_t batch_id = params->global_batch_id;
+    mode_ = env->GetCurrentMode(batch_id);
+    memorypool_->SetCurrentMode(mode_);
+    memorypool_->SetIter(env->GetLocalBatchId(batch_id));
+    memorypool_->SetGlobalBatchId(batch_id);
+    env->IPCWait(local_dev_id_, current_pipe_);
+    for (int i = 0; i < op_num_; i++) {
+      if (i % INTRABATCH_CON >= 1)  // lookup / io ops wait for the sampling op of their hop (server.cu:312-314)
+        LGCHECK(lg_stream_wait_event(streams_[i % INTRABATCH_CON], events_[i / INTRABATCH_CON * INTRABATCH_CON]));
+      op_params_[i]->is_presc = false;
+      ops_[i]->run(op_params_[i]);
+    }
+    for (int i = op_num_ - INTRABATCH_CON; i < op_num_; i++)  // join all three streams before the hand-off
+      LGCHECK(lg_event_synchronize(events_[i]));
+    int32_t st = 0;
+    LGCHECK(lg_sampler_status(memorypool_->sampler, streams_[0], &st));
+    if (st != 0) {
+      std::fprintf(stderr, "batch %d on GPU %d overflowed its buffers (status %d)\n", batch_id, local_dev_id_, st);
+      std::exit(EXIT_FAILURE);
+    }
+    env->IPCPost(local_dev_id_, current_pipe_);
+    if (batch_id % 1000 == 0 && local_dev_id_ == 0) std::cout << "batch id: " << batch_id << "\n" << std::flush;
+    current_pipe_ = (current_pipe_ + 1) % interbatch_concurrency_;
+    memorypool_->SetCurrentPipe(current_pipe_);
+  }
+
+  void Finalize(RunnerParams* params) override {
+    auto* env = (IPCEnv*)params->env;
+    env->IPCWait(local_dev_id_, (current_pipe_ + 1) % interbatch_concurrency_);  // server.cu:336
+    LGCHECK(lg_set_device(local_dev_id_));
+    lg_sampler_destroy(memorypool_->sampler);
+    for (auto& e : events_) lg_event_destroy(e);
+    for (auto& s : streams_) lg_stream_destroy(s);
+  }
+
+ private:
+  int32_t num_ids_ = 0, float_feature_len_ = 0, max_batch_ = 0;
+  MemoryPool* memorypool_ = nullptr;
+  int current_pipe_ = 0, interbatch_concurrency_ = INTERBATCH_CON, local_dev_id_ = 0, mode_ = 0, op_num_ = 0;
+  std::vector<lg_stream_t> streams_;
+  std::vector<lg_event_t> events_;
+  std::vector<Operator*> ops_;
+  std::vector<OpParams*> op_params_;
+};
+}  // namespace
+
+Server* NewGPUServer() { return new GPUServer(); }
+Runner* NewGPURunner() { return new GPURunner(); }
