@@ -115,9 +115,14 @@ int lg_sampler_set_table_slots(lg_sampler* s, int64_t slots);
 int64_t lg_sampler_scratch_bytes(const lg_sampler* s);
 /* data mover used by lg_feature_cache_lookup: LG_GATHER_AUTO / LG_GATHER_LDG / LG_GATHER_TMA */
 int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant);
-/* lg_run_batch runs the gathers on an internal side stream so that they overlap the sampling of
- * the next hop (default on); 0 = strictly one stream */
-int lg_sampler_set_overlap(lg_sampler* s, int32_t on);
+/* how lg_run_batch schedules the gathers: 0 = everything on the caller's stream; 1 (default) = gathers
+ * on an internal side stream, overlapping the sampling of the next hop, joined before returning
+ * (the reference's stream split, engine/server.cu:311-317); 2 = pipelined across batches like the
+ * reference's two INTERBATCH_CON slots: the last gather of batch k overlaps the sampling of batch
+ * k+1; a consumer (or anyone reusing the buffers on another stream) calls lg_batch_wait first. */
+int lg_sampler_set_overlap(lg_sampler* s, int32_t mode);
+/* make `stream` wait until the batch last produced into `batch` is complete (mode 2; no-op otherwise) */
+int lg_batch_wait(lg_sampler* s, lg_stream_t stream, const lg_batch* batch);
 /* sticky overflow status (0 ok, 1 ids overflow, 2 features buffer too small — the reference
  * sizes it 1.2 x presampled max without a bound check, engine/server.cu:277).  Synchronises. */
 int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);

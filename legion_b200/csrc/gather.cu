@@ -125,16 +125,22 @@ __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
   row_range(a, &off, &cnt);
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * 32;
   const int dim = a.cache.dim;
   int32_t t0 = 0, t1 = 0, t2 = 0;
   u64 pol_first = 0, pol_last = 0;
   if (HINT >= 1) pol_first = policy_evict_first();
   if (HINT >= 2) pol_last = policy_evict_last();
-  for (int64_t r0 = warp_global * R; r0 < cnt; r0 += n_warps * R) {
+
+  // A warp owns 32 consecutive rows per iteration: every lane resolves ONE row (id -> directory ->
+  // source pointer, two dependent loads), then the warp streams the rows R at a time.  The lookups of
+  // the NEXT 32 rows are issued before the current rows are moved, so the dependent-load chain is off
+  // the critical path (it was the limiter of the first version: 3 serial latencies per 4 rows).
+  auto resolve = [&](int64_t base) -> u64 {
     u64 src = 0;  // bit 0 = hot row
-    if (lane < R && r0 + lane < cnt) {
-      int64_t row = off + r0 + lane;
+    const int64_t r = base + lane;
+    if (r < cnt) {
+      const int64_t row = off + r;
       if (row < a.dst_rows) {
         int t;
         bool hot;
@@ -147,42 +153,55 @@ __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
         *a.status = 2;
       }
     }
+    return src;
+  };
+
+  int64_t base = warp_global * 32;
+  u64 cur = (base < cnt) ? resolve(base) : 0;
+  for (; base < cnt; base += stride) {
+    const int64_t nbase = base + stride;
+    u64 nxt = 0;
+    if (nbase < cnt) nxt = resolve(nbase);
+    const int rows_here = (cnt - base < 32) ? (int)(cnt - base) : 32;
     if (VEC4) {
       const int d4 = dim >> 2;
-      for (int c0 = 0; c0 < d4; c0 += 32) {
-        const int c = c0 + lane;
-        float4 v[R];
-        u64 sk[R];
+      for (int g = 0; g < rows_here; g += R) {
+        for (int c0 = 0; c0 < d4; c0 += 32) {
+          const int c = c0 + lane;
+          float4 v[R];
+          u64 sk[R];
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-          sk[k] = __shfl_sync(0xffffffffu, src, k);
-          if (sk[k] && c < d4) {
-            const float* p = (const float*)(sk[k] & ~1ull) + 4 * c;
-            if (HINT >= 2)
-              v[k] = ld_nc_v4_hint(p, (sk[k] & 1ull) ? pol_last : pol_first);
-            else
-              v[k] = ld_nc_v4(p);
+          for (int k = 0; k < R; k++) {
+            sk[k] = __shfl_sync(0xffffffffu, cur, (g + k) & 31);
+            if (g + k >= rows_here) sk[k] = 0;
+            if (sk[k] && c < d4) {
+              const float* p = (const float*)(sk[k] & ~1ull) + 4 * c;
+              if (HINT >= 2)
+                v[k] = ld_nc_v4_hint(p, (sk[k] & 1ull) ? pol_last : pol_first);
+              else
+                v[k] = ld_nc_v4(p);
+            }
           }
+#pragma unroll
+          for (int k = 0; k < R; k++)
+            if (sk[k] && c < d4) {
+              float* d = a.dst + (off + base + g + k) * dim + 4 * c;
+              if (HINT >= 1)
+                st_v4_hint(d, v[k], pol_first);
+              else
+                st_v4(d, v[k]);
+            }
         }
-#pragma unroll
-        for (int k = 0; k < R; k++)
-          if (sk[k] && c < d4) {
-            float* d = a.dst + (off + r0 + k) * dim + 4 * c;
-            if (HINT >= 1)
-              st_v4_hint(d, v[k], pol_first);
-            else
-              st_v4(d, v[k]);
-          }
       }
     } else {
-#pragma unroll
-      for (int k = 0; k < R; k++) {
-        const float* s = (const float*)(__shfl_sync(0xffffffffu, src, k) & ~1ull);
+      for (int g = 0; g < rows_here; g++) {
+        const float* s = (const float*)(__shfl_sync(0xffffffffu, cur, g) & ~1ull);
         if (!s) continue;
-        float* d = a.dst + (off + r0 + k) * dim;
+        float* d = a.dst + (off + base + g) * dim;
         for (int c = lane; c < dim; c += 32) d[c] = __ldg(s + c);
       }
     }
+    cur = nxt;
   }
   tier_flush(a, t0, t1, t2, lane);
 }
@@ -250,28 +269,35 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
+  auto resolve = [&](int64_t it) -> const float* {
+    const float* src = nullptr;
+    const int64_t tile = blockIdx.x + it * gridDim.x;
+    const int64_t r = tile * kTmaRows + lane;
+    if (it < my_tiles && r < cnt) {
+      const int64_t row = off + r;
+      if (row < a.dst_rows) {
+        int t;
+        bool hot;
+        src = locate(a, a.ids[row], &t, &hot);
+        t0 += (t == 0);
+        t1 += (t == 1);
+        t2 += (t == 2);
+      } else {
+        *a.status = 2;
+      }
+    }
+    return src;
+  };
+  const float* src = resolve(0);
   for (int64_t it = 0; it < my_tiles + LAG; it++) {
+    // the id -> directory -> pointer chain of the NEXT tile is issued now and consumed one iteration later
+    const float* src_next = resolve(it + 1);
     if (it < my_tiles) {
       const int s = (int)(it % STAGES);
-      const int64_t tile = blockIdx.x + it * gridDim.x;
-      const int64_t row = off + tile * kTmaRows + lane;
       // stage s was read by the store of tile(it - STAGES), issued two iterations ago: only the
       // store issued in the previous iteration may still be reading shared memory
       bulk_wait_read<1>();
       __syncwarp();
-      const float* src = nullptr;
-      if (tile * kTmaRows + lane < cnt) {
-        if (row < a.dst_rows) {
-          int t;
-          bool hot;
-          src = locate(a, a.ids[row], &t, &hot);
-          t0 += (t == 0);
-          t1 += (t == 1);
-          t2 += (t == 2);
-        } else {
-          *a.status = 2;
-        }
-      }
       const unsigned valid = __ballot_sync(0xffffffffu, src != nullptr);
       const uint32_t bar = smem_u32(&bars[s]);
       if (lane == 0) {
@@ -281,6 +307,7 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
       __syncwarp();
       if (src) bulk_g2s(smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), src, row_bytes, bar);
     }
+    src = src_next;
     const int64_t dt = it - LAG;
     if (dt >= 0 && dt < my_tiles) {
       const int s = (int)(dt % STAGES);
@@ -315,7 +342,7 @@ struct Tune {
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{4, 0, 4, 64, 8};
+    Tune x{8, 0, 3, 64, 8};
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_LDG_HINT")) x.ldg_hint = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
@@ -343,7 +370,7 @@ int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
 
 template <int R, int HINT>
 int launch_ldg(cudaStream_t st, const GatherArgs& a, int64_t max_rows, bool vec_ok) {
-  int64_t warps = (max_rows + R - 1) / R;
+  int64_t warps = (max_rows + 31) / 32;  // a warp owns 32 rows per iteration
   int64_t grid = (warps + 7) / 8;
   const int64_t cap = (int64_t)kSMs * tune().ldg_ctas;  // resident CTAs per SM x 148, grid-stride beyond
   if (grid > cap) grid = cap;
@@ -377,12 +404,11 @@ int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) 
     case 20: return launch_ldg<2, 0>(st, a, max_rows, vec_ok);
     case 21: return launch_ldg<2, 1>(st, a, max_rows, vec_ok);
     case 22: return launch_ldg<2, 2>(st, a, max_rows, vec_ok);
+    case 40: return launch_ldg<4, 0>(st, a, max_rows, vec_ok);
     case 41: return launch_ldg<4, 1>(st, a, max_rows, vec_ok);
     case 42: return launch_ldg<4, 2>(st, a, max_rows, vec_ok);
-    case 80: return launch_ldg<8, 0>(st, a, max_rows, vec_ok);
-    case 81: return launch_ldg<8, 1>(st, a, max_rows, vec_ok);
-    case 82: return launch_ldg<8, 2>(st, a, max_rows, vec_ok);
-    default: return launch_ldg<4, 0>(st, a, max_rows, vec_ok);
+    case 160: return launch_ldg<16, 0>(st, a, max_rows, vec_ok);
+    default: return launch_ldg<8, 0>(st, a, max_rows, vec_ok);
   }
 }
 

@@ -457,6 +457,7 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaStreamDestroy(s->side);
   for (int h = 0; h <= LG_MAX_HOPS; h++) cudaEventDestroy(s->ev_fork[h]);
   cudaEventDestroy(s->ev_join);
+  for (int i = 0; i < s->n_done; i++) cudaEventDestroy(s->done[i].ev);
   delete s;
   return 0;
 }
@@ -477,9 +478,35 @@ extern "C" int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant) {
   return 0;
 }
 
-extern "C" int lg_sampler_set_overlap(lg_sampler* s, int32_t on) {
+extern "C" int lg_sampler_set_overlap(lg_sampler* s, int32_t mode) {
   LG_REQUIRE(s, "null sampler");
-  s->overlap = on ? 1 : 0;
+  LG_REQUIRE(mode >= 0 && mode <= 2, "overlap mode %d", mode);
+  s->overlap = mode;
+  return 0;
+}
+
+static int done_event(lg_sampler* s, const lg_batch* b, bool create, cudaEvent_t* ev) {
+  *ev = nullptr;
+  for (int i = 0; i < s->n_done; i++)
+    if (s->done[i].key == b->ids) {
+      *ev = s->done[i].ev;
+      return 0;
+    }
+  if (!create) return 0;
+  LG_REQUIRE(s->n_done < 4, "pipelined mode supports at most 4 distinct batch buffer sets");
+  LG_CUDA(cudaEventCreateWithFlags(&s->done[s->n_done].ev, cudaEventDisableTiming));
+  s->done[s->n_done].key = b->ids;
+  *ev = s->done[s->n_done].ev;
+  s->n_done++;
+  return 0;
+}
+
+extern "C" int lg_batch_wait(lg_sampler* s, lg_stream_t stream, const lg_batch* b) {
+  LG_REQUIRE(s && b, "lg_batch_wait: null argument");
+  cudaEvent_t ev;
+  int rc = done_event(s, b, false, &ev);
+  if (rc) return rc;
+  if (ev) LG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
   return 0;
 }
 
@@ -601,6 +628,13 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
   LG_REQUIRE(s && topo && p && b, "lg_run_batch: null argument");
   cudaStream_t main_st = (cudaStream_t)stream;
   const bool fork = cache && s->overlap;
+  const bool pipelined = cache && s->overlap == 2;
+  cudaEvent_t ev_done = nullptr;
+  if (pipelined) {  // these buffers may still be written by the gathers of the batch that used them last
+    int rc0 = done_event(s, b, true, &ev_done);
+    if (rc0) return rc0;
+    LG_CUDA(cudaStreamWaitEvent(main_st, ev_done, 0));
+  }
   // gathers go to the side stream (HBM-bound) while the next hop is sampled on the caller's stream
   // (latency-bound): both kinds of kernels are resident on the SMs at once.
   lg_stream_t gst = fork ? (lg_stream_t)s->side : stream;
@@ -623,7 +657,9 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
     rc = lg_feature_cache_lookup(s, gst, cache, hop * LG_INTRABATCH_CON + 1, p->local_part, b, tier_rows);
     if (rc) return rc;
   }
-  if (fork) {  // join: the batch is complete on the caller's stream
+  if (pipelined) {  // no join: the next batch is sampled while this batch's last gather streams
+    LG_CUDA(cudaEventRecord(ev_done, s->side));
+  } else if (fork) {  // join: the batch is complete on the caller's stream
     LG_CUDA(cudaEventRecord(s->ev_join, s->side));
     LG_CUDA(cudaStreamWaitEvent(main_st, s->ev_join, 0));
   }

@@ -35,5 +35,11 @@ struct lg_sampler {
   cudaStream_t side;
   cudaEvent_t ev_fork[LG_MAX_HOPS + 1];
   cudaEvent_t ev_join;
-  int32_t overlap;
+  int32_t overlap;  // 0 one stream, 1 fork/join inside a batch, 2 pipelined across batches (see lg_batch_wait)
+  // pipelined mode: completion event of the last batch that used a given set of buffers
+  struct Done {
+    const void* key;  // batch->ids
+    cudaEvent_t ev;
+  } done[4];
+  int32_t n_done;
 };

@@ -330,8 +330,12 @@ class DataPath:
         check(self.L.lg_sampler_status(self.sampler, self._stream(), C.byref(s)))
         return s.value
 
-    def set_overlap(self, on):
-        check(self.L.lg_sampler_set_overlap(self.sampler, 1 if on else 0))
+    def set_overlap(self, mode):
+        """0 one stream, 1 gathers overlap the next hop (joined per batch), 2 pipelined across batches"""
+        check(self.L.lg_sampler_set_overlap(self.sampler, int(mode)))
+
+    def batch_wait(self, buf):
+        check(self.L.lg_batch_wait(self.sampler, self._stream(), C.byref(buf.c)))
 
     def set_gather_variant(self, v):
         check(self.L.lg_sampler_set_gather_variant(self.sampler, v))

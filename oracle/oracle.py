@@ -43,6 +43,7 @@ def lib():
     L.lgo_state_create.restype = C.c_void_p
     L.lgo_state_create.argtypes = [C.c_int64]
     L.lgo_state_destroy.argtypes = [C.c_void_p]
+    L.lgo_state_load.argtypes = [C.c_void_p, i32p, C.c_int32]
     L.lgo_batch_generate.argtypes = [C.c_void_p, i32p, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      i32p, i32p, i32p, i32p]
     L.lgo_random_sample.argtypes = [C.c_void_p, i64p, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,

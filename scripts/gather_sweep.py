@@ -73,21 +73,18 @@ def main():
         pass
     matrix = []
     for dim in (100, 128):
-        for pattern in ("seq", "rand", "skew"):
+        for pattern in ("seq", "skew"):
             matrix.append(dict(SW_DIM=dim, SW_PATTERN=pattern, SW_VARIANT=1))
             matrix.append(dict(SW_DIM=dim, SW_PATTERN=pattern, SW_VARIANT=2))
-    for r in (2, 8):
+    for r in (4, 16):
         matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_R=r))
-    for ctas in (4, 6):
+    for ctas in (3, 4, 6):
         matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_CTAS=ctas))
-    for hint in (1, 2):
-        for flushed in (1, 0):
-            matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_HINT=hint, SW_FLUSH=flushed))
+    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_R=4, LG_LDG_CTAS=4))
     matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, SW_FLUSH=0))
-    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_HINT=2, LG_HOT_MB=96, SW_FLUSH=0))
-    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_HINT=2, LG_LDG_R=8, SW_FLUSH=0))
-    for stages in (3, 6, 8):
+    for stages in (4, 6):
         matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=2, LG_TMA_STAGES=stages))
+    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, SW_CACHED=0))
     print(f"{'config':70s} {'ms':>8s} {'GB/s':>8s} {'frac':>6s} ok")
     for cfg in matrix:
         env = dict(os.environ, **{k: str(v) for k, v in cfg.items()})

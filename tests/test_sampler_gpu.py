@@ -243,3 +243,31 @@ def test_distribution_fanout_and_uniformity(oracle):
         inc_dgl += np.bincount(base.ids[base.src[:e]], minlength=degv)
     inc_dgl /= 50 * N
     assert abs(inc_dgl.mean() - c / degv) < 1e-9 and np.abs(inc_dgl - c / degv).max() < 0.05
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_stream_schedules_give_identical_batches(oracle, mode):
+    """one stream / gather overlapping the next hop / pipelined over two buffer slots: same bits"""
+    indptr, indices = small_graph(3000, 14.0, 400)
+    N = len(indptr) - 1
+    feat = _feat(N, 100)
+    ids, labels = make_sets(N)
+    fanout, B = [10, 5], 128
+    rig = Rig(indptr, indices, feat, fanout, B)
+    rig.dp.set_overlap(mode)
+    d_ids, d_lab = rig.sets(ids, labels)
+    bufs = [rig.dp.alloc_batch(), rig.dp.alloc_batch()]
+    orc = oracle.Oracle(indptr, indices, fanout, B)
+    n_batches = 8
+    for it in range(n_batches):
+        rig.dp.run_once(rig.dp.params(d_ids, d_lab, B, it, seed=17, batch_id=it), bufs[it % 2])
+        if it >= 1:  # consume the previous batch while this one is in flight (what the trainer does)
+            prev = bufs[(it - 1) % 2]
+            rig.dp.batch_wait(prev)
+            torch.cuda.current_stream().synchronize()
+            want = orc.run_batch(ids, labels, B, it - 1, seed=17, batch_id=it - 1)
+            assert_batch_equal(prev.to_host(2), want, 2, feat)
+    rig.dp.batch_wait(bufs[(n_batches - 1) % 2])
+    torch.cuda.synchronize()
+    want = orc.run_batch(ids, labels, B, n_batches - 1, seed=17, batch_id=n_batches - 1)
+    assert_batch_equal(bufs[(n_batches - 1) % 2].to_host(2), want, 2, feat)
