@@ -125,22 +125,16 @@ __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
   row_range(a, &off, &cnt);
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * 32;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int dim = a.cache.dim;
   int32_t t0 = 0, t1 = 0, t2 = 0;
   u64 pol_first = 0, pol_last = 0;
   if (HINT >= 1) pol_first = policy_evict_first();
   if (HINT >= 2) pol_last = policy_evict_last();
-
-  // A warp owns 32 consecutive rows per iteration: every lane resolves ONE row (id -> directory ->
-  // source pointer, two dependent loads), then the warp streams the rows R at a time.  The lookups of
-  // the NEXT 32 rows are issued before the current rows are moved, so the dependent-load chain is off
-  // the critical path (it was the limiter of the first version: 3 serial latencies per 4 rows).
-  auto resolve = [&](int64_t base) -> u64 {
+  for (int64_t r0 = warp_global * R; r0 < cnt; r0 += n_warps * R) {
     u64 src = 0;  // bit 0 = hot row
-    const int64_t r = base + lane;
-    if (r < cnt) {
-      const int64_t row = off + r;
+    if (lane < R && r0 + lane < cnt) {
+      int64_t row = off + r0 + lane;
       if (row < a.dst_rows) {
         int t;
         bool hot;
@@ -153,55 +147,42 @@ __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
         *a.status = 2;
       }
     }
-    return src;
-  };
-
-  int64_t base = warp_global * 32;
-  u64 cur = (base < cnt) ? resolve(base) : 0;
-  for (; base < cnt; base += stride) {
-    const int64_t nbase = base + stride;
-    u64 nxt = 0;
-    if (nbase < cnt) nxt = resolve(nbase);
-    const int rows_here = (cnt - base < 32) ? (int)(cnt - base) : 32;
     if (VEC4) {
       const int d4 = dim >> 2;
-      for (int g = 0; g < rows_here; g += R) {
-        for (int c0 = 0; c0 < d4; c0 += 32) {
-          const int c = c0 + lane;
-          float4 v[R];
-          u64 sk[R];
+      for (int c0 = 0; c0 < d4; c0 += 32) {
+        const int c = c0 + lane;
+        float4 v[R];
+        u64 sk[R];
 #pragma unroll
-          for (int k = 0; k < R; k++) {
-            sk[k] = __shfl_sync(0xffffffffu, cur, (g + k) & 31);
-            if (g + k >= rows_here) sk[k] = 0;
-            if (sk[k] && c < d4) {
-              const float* p = (const float*)(sk[k] & ~1ull) + 4 * c;
-              if (HINT >= 2)
-                v[k] = ld_nc_v4_hint(p, (sk[k] & 1ull) ? pol_last : pol_first);
-              else
-                v[k] = ld_nc_v4(p);
-            }
+        for (int k = 0; k < R; k++) {
+          sk[k] = __shfl_sync(0xffffffffu, src, k);
+          if (sk[k] && c < d4) {
+            const float* p = (const float*)(sk[k] & ~1ull) + 4 * c;
+            if (HINT >= 2)
+              v[k] = ld_nc_v4_hint(p, (sk[k] & 1ull) ? pol_last : pol_first);
+            else
+              v[k] = ld_nc_v4(p);
           }
-#pragma unroll
-          for (int k = 0; k < R; k++)
-            if (sk[k] && c < d4) {
-              float* d = a.dst + (off + base + g + k) * dim + 4 * c;
-              if (HINT >= 1)
-                st_v4_hint(d, v[k], pol_first);
-              else
-                st_v4(d, v[k]);
-            }
         }
+#pragma unroll
+        for (int k = 0; k < R; k++)
+          if (sk[k] && c < d4) {
+            float* d = a.dst + (off + r0 + k) * dim + 4 * c;
+            if (HINT >= 1)
+              st_v4_hint(d, v[k], pol_first);
+            else
+              st_v4(d, v[k]);
+          }
       }
     } else {
-      for (int g = 0; g < rows_here; g++) {
-        const float* s = (const float*)(__shfl_sync(0xffffffffu, cur, g) & ~1ull);
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        const float* s = (const float*)(__shfl_sync(0xffffffffu, src, k) & ~1ull);
         if (!s) continue;
-        float* d = a.dst + (off + base + g) * dim;
+        float* d = a.dst + (off + r0 + k) * dim;
         for (int c = lane; c < dim; c += 32) d[c] = __ldg(s + c);
       }
     }
-    cur = nxt;
   }
   tier_flush(a, t0, t1, t2, lane);
 }
@@ -269,29 +250,39 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  auto resolve = [&](int64_t it) -> const float* {
-    const float* src = nullptr;
+  // The id -> directory -> pointer chain is software-pipelined so that no iteration waits on it:
+  // ids are loaded two tiles ahead, directory entries one tile ahead, pointers are formed at use.
+  auto load_id = [&](int64_t it) -> int32_t {
     const int64_t tile = blockIdx.x + it * gridDim.x;
     const int64_t r = tile * kTmaRows + lane;
-    if (it < my_tiles && r < cnt) {
-      const int64_t row = off + r;
-      if (row < a.dst_rows) {
-        int t;
-        bool hot;
-        src = locate(a, a.ids[row], &t, &hot);
-        t0 += (t == 0);
-        t1 += (t == 1);
-        t2 += (t == 2);
-      } else {
-        *a.status = 2;
-      }
+    if (it >= my_tiles || r >= cnt) return -1;
+    if (off + r >= a.dst_rows) {
+      *a.status = 2;
+      return -1;
     }
-    return src;
+    return a.ids[off + r];
   };
-  const float* src = resolve(0);
+  auto load_loc = [&](int32_t id) -> int32_t {
+    if (id < 0 || !a.cache.directory || id >= a.cache.num_nodes) return LG_CACHEMISS_FLAG;
+    return a.cache.directory[id];
+  };
+  auto form_ptr = [&](int32_t id, int32_t gidx) -> const float* {
+    if (id < 0) return nullptr;  // -1 padding / out of range rows are skipped (cache_impl.cuh:263-264)
+    if (gidx < 0) {              // miss -> backing matrix (cache_impl.cuh:262-266)
+      t2++;
+      return a.cache.backing + (int64_t)(id % a.cache.num_nodes) * a.cache.dim;
+    }
+    const int32_t didx = gidx / a.cache.shard_rows;  // cache_impl.cuh:259-260
+    const int32_t fidx = gidx - didx * a.cache.shard_rows;
+    if (didx == a.local_part) t0++; else t1++;
+    return a.cache.shard[didx] + (int64_t)fidx * a.cache.dim;
+  };
+  int32_t id0 = load_id(0), id1 = load_id(1);
+  int32_t loc0 = load_loc(id0);
   for (int64_t it = 0; it < my_tiles + LAG; it++) {
-    // the id -> directory -> pointer chain of the NEXT tile is issued now and consumed one iteration later
-    const float* src_next = resolve(it + 1);
+    const int32_t id2 = load_id(it + 2);
+    const int32_t loc1 = load_loc(id1);
+    const float* src = form_ptr(id0, loc0);
     if (it < my_tiles) {
       const int s = (int)(it % STAGES);
       // stage s was read by the store of tile(it - STAGES), issued two iterations ago: only the
@@ -307,7 +298,9 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
       __syncwarp();
       if (src) bulk_g2s(smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), src, row_bytes, bar);
     }
-    src = src_next;
+    id0 = id1;
+    id1 = id2;
+    loc0 = loc1;
     const int64_t dt = it - LAG;
     if (dt >= 0 && dt < my_tiles) {
       const int s = (int)(dt % STAGES);
@@ -342,7 +335,7 @@ struct Tune {
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 0, 3, 64, 8};
+    Tune x{8, 0, 3, 64, 8};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM)
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_LDG_HINT")) x.ldg_hint = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
@@ -370,7 +363,7 @@ int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
 
 template <int R, int HINT>
 int launch_ldg(cudaStream_t st, const GatherArgs& a, int64_t max_rows, bool vec_ok) {
-  int64_t warps = (max_rows + 31) / 32;  // a warp owns 32 rows per iteration
+  int64_t warps = (max_rows + R - 1) / R;
   int64_t grid = (warps + 7) / 8;
   const int64_t cap = (int64_t)kSMs * tune().ldg_ctas;  // resident CTAs per SM x 148, grid-stride beyond
   if (grid > cap) grid = cap;
@@ -388,7 +381,7 @@ int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) 
   const bool vec_ok = (dim % 4 == 0) && (((uintptr_t)a.dst & 15) == 0) && (((uintptr_t)a.cache.backing & 15) == 0);
   const Tune& t = tune();
   a.hot_rows = (int32_t)(((int64_t)t.hot_mb << 20) / ((int64_t)dim * 4));
-  if (variant == LG_GATHER_AUTO) variant = LG_GATHER_LDG;
+  if (variant == LG_GATHER_AUTO) variant = LG_GATHER_TMA;  // falls through to LDG when rows are not 16-byte multiples
   if (variant == LG_GATHER_TMA && vec_ok && (size_t)dim * 4 * kTmaRows * 3 <= 200 * 1024) {
     int stages = t.tma_stages;
     while (stages > 3 && (size_t)dim * 4 * kTmaRows * stages > 200 * 1024) stages--;
@@ -407,7 +400,6 @@ int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) 
     case 40: return launch_ldg<4, 0>(st, a, max_rows, vec_ok);
     case 41: return launch_ldg<4, 1>(st, a, max_rows, vec_ok);
     case 42: return launch_ldg<4, 2>(st, a, max_rows, vec_ok);
-    case 160: return launch_ldg<16, 0>(st, a, max_rows, vec_ok);
     default: return launch_ldg<8, 0>(st, a, max_rows, vec_ok);
   }
 }

@@ -30,7 +30,7 @@ constexpr int kBlock = 256;
 constexpr int kRankItems = 4;                      // edges per thread in rank_relabel_kernel
 constexpr int kRankTile = kBlock * kRankItems;     // 1024 edges per tile
 static_assert(kRankItems * (kBlock / 32) == 32, "rank tile partial counts must fill one warp");
-constexpr int kMaxTilesPerHop = 1 << 16;
+constexpr int kSlotUnroll = 4;                     // neighbour reads in flight per thread in sample_hop_kernel
 
 __device__ __forceinline__ void table_insert_min(u64* table, uint32_t mask, int32_t key, uint32_t val) {
   uint32_t slot = hash32((uint32_t)key) & mask;
@@ -206,18 +206,34 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
   __syncthreads();
   const int32_t base = s_base;
 
-  // 4. one thread per slot: pick, emit, insert-min
+  // 4. one thread per slot: pick, emit, insert-min.  kSlotUnroll independent neighbour reads are issued
+  //    back to back before any of them is consumed (the read is a random 4-byte HBM/NVLink/PCIe access).
   const int n_slots = TILE_F * c;
-  for (int k = tid; k < n_slots; k += kBlock) {
-    int t = k / c, j = k - t * c;
-    if (j < s_cnt[t]) {  // :232  neighbor_offset >= col_size -> none
-      uint32_t slot = (uint32_t)(i0 + t) * (uint32_t)c + (uint32_t)j;
-      int32_t pick = pick_neighbor<RNG>(slot, s_deg[t], (uint32_t)a.hop, a.batch_id, a.stream_id, a.k0, a.k1);
-      int32_t w = s_indices[t][s_start[t] + pick];  // :240-242
-      int32_t p = base + s_off[t] + j;
-      a.gid_out[p] = w;
-      a.agg_dst[edge_base + p] = s_flocal[t];  // construct_graph :292,294
-      table_insert_min(a.table, a.mask, w, kNewBit | (uint32_t)p);
+  for (int k0 = tid; k0 < n_slots; k0 += kBlock * kSlotUnroll) {
+    int32_t w[kSlotUnroll], p[kSlotUnroll], fl[kSlotUnroll];
+#pragma unroll
+    for (int u = 0; u < kSlotUnroll; u++) {
+      const int k = k0 + u * kBlock;
+      p[u] = -1;
+      if (k < n_slots) {
+        const int t = k / c, j = k - t * c;
+        if (j < s_cnt[t]) {  // :232  neighbor_offset >= col_size -> none
+          const uint32_t slot = (uint32_t)(i0 + t) * (uint32_t)c + (uint32_t)j;
+          const int32_t pick =
+              pick_neighbor<RNG>(slot, s_deg[t], (uint32_t)a.hop, a.batch_id, a.stream_id, a.k0, a.k1);
+          w[u] = __ldg(s_indices[t] + s_start[t] + pick);  // :240-242
+          p[u] = base + s_off[t] + j;
+          fl[u] = s_flocal[t];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSlotUnroll; u++) {
+      if (p[u] >= 0) {
+        a.gid_out[p[u]] = w[u];
+        a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
+        table_insert_min(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u]);
+      }
     }
   }
 }

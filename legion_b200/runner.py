@@ -271,17 +271,16 @@ class DataPath:
 
     def _exchange(self, raw, nbytes, kg, j, dist, nbytes_own=None):
         """all-gather CUDA IPC handles of one buffer per clique member; returns the kg device pointers"""
+        from .multigpu import exchange_handles
         assert dist is not None and dist.is_initialized(), "multi-GPU cache needs torch.distributed"
         mine = (raw.ipc_handle(), nbytes if nbytes is not None else nbytes_own)
-        allh = [None] * dist.get_world_size()
-        dist.all_gather_object(allh, mine)
+        clique = exchange_handles(dist, mine, self.rank, kg)
         ptrs = []
-        base = (self.rank // kg) * kg  # first rank of this NVLink clique (Kc cliques of Kg GPUs)
         for p in range(kg):
             if p == j:
                 ptrs.append(raw.ptr)
             else:
-                h, nb = allh[base + p]
+                h, nb = clique[p]
                 peer = RawDeviceBuffer.from_ipc(h, nb, self.device)
                 self._keep.append(peer)
                 ptrs.append(peer.ptr)

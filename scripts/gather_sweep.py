@@ -74,17 +74,13 @@ def main():
     matrix = []
     for dim in (100, 128):
         for pattern in ("seq", "skew"):
-            matrix.append(dict(SW_DIM=dim, SW_PATTERN=pattern, SW_VARIANT=1))
             matrix.append(dict(SW_DIM=dim, SW_PATTERN=pattern, SW_VARIANT=2))
-    for r in (4, 16):
-        matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_R=r))
-    for ctas in (3, 4, 6):
-        matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_CTAS=ctas))
-    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_R=4, LG_LDG_CTAS=4))
-    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, SW_FLUSH=0))
+    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1))
+    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, LG_LDG_R=4))
     for stages in (4, 6):
         matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=2, LG_TMA_STAGES=stages))
-    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=1, SW_CACHED=0))
+    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=2, SW_CACHED=0))
+    matrix.append(dict(SW_DIM=100, SW_PATTERN="skew", SW_VARIANT=2, SW_FLUSH=0))
     print(f"{'config':70s} {'ms':>8s} {'GB/s':>8s} {'frac':>6s} ok")
     for cfg in matrix:
         env = dict(os.environ, **{k: str(v) for k, v in cfg.items()})
