@@ -155,14 +155,17 @@ class GPURunner : public Runner {
       b->num_ids = num_ids_;
       b->feature_rows = 0;
     }
-    events_.resize(op_num_);
+    events_.resize(interbatch_concurrency_);
+    for (auto& ev : events_) {
+      ev.resize(op_num_);
+      for (auto& e : ev) LGCHECK(lg_event_create(&e));
+    }
     op_params_.resize(op_num_);
     for (int i = 0; i < op_num_; i++) {
       auto* op = new OpParams();
       op->device_id = local_dev_id_;
       op->stream = streams_[i % INTRABATCH_CON];
-      LGCHECK(lg_event_create(&events_[i]));
-      op->event = events_[i];
+      op->event = events_[0][i];
       op->memorypool = memorypool_;
       op->cache = cache;
       op->graph = params->graph;
@@ -198,13 +201,18 @@ class GPURunner : public Runner {
     memorypool_->SetCurrentMode(TRAINMODE);
     memorypool_->SetIter(params->global_batch_id);
     memorypool_->SetGlobalBatchId(params->global_batch_id);
+    memorypool_->SetCurrentPipe(0);
     for (int i = 0; i < op_num_; i += INTRABATCH_CON) {  // ops 0,3,6,..: all on stream 0
       op_params_[i]->is_presc = true;
+      op_params_[i]->event = events_[0][i];
       ops_[i]->run(op_params_[i]);
     }
-    LGCHECK(lg_event_synchronize(op_params_[op_num_ - 1]->event));
+    LGCHECK(lg_event_synchronize(events_[0][op_num_ - 1]));
   }
 
+  // RunOnce(i) launches batch i and then completes batch i-1 (host-level software pipeline over the
+  // INTERBATCH_CON slots): the gather tail of batch i-1 (stream 1) overlaps the sampling of batch i
+  // (stream 0).  The trainer still sees batches strictly in order, one semaphore post per batch.
   void RunOnce(RunnerParams* params) override {
     LGCHECK(lg_set_device(local_dev_id_));
     auto* env = (IPCEnv*)params->env;
@@ -213,33 +221,50 @@ class GPURunner : public Runner {
     memorypool_->SetCurrentMode(mode_);
     memorypool_->SetIter(env->GetLocalBatchId(batch_id));
     memorypool_->SetGlobalBatchId(batch_id);
+    memorypool_->SetCurrentPipe(current_pipe_);
     env->IPCWait(local_dev_id_, current_pipe_);
+    auto& ev = events_[current_pipe_];
     for (int i = 0; i < op_num_; i++) {
       if (i % INTRABATCH_CON >= 1)  // lookup / io ops wait for the sampling op of their hop (server.cu:312-314)
-        LGCHECK(lg_stream_wait_event(streams_[i % INTRABATCH_CON], events_[i / INTRABATCH_CON * INTRABATCH_CON]));
+        LGCHECK(lg_stream_wait_event(streams_[i % INTRABATCH_CON], ev[i / INTRABATCH_CON * INTRABATCH_CON]));
       op_params_[i]->is_presc = false;
+      op_params_[i]->event = ev[i];
       ops_[i]->run(op_params_[i]);
     }
+    if (pending_pipe_ >= 0) Complete(env, pending_pipe_, pending_batch_);
+    pending_pipe_ = current_pipe_;
+    pending_batch_ = batch_id;
+    current_pipe_ = (current_pipe_ + 1) % interbatch_concurrency_;
+    if (batch_id == env->GetMaxStep() - 1) {  // last batch: nothing left to overlap with, hand it off from this thread
+      Complete(env, pending_pipe_, pending_batch_);
+      pending_pipe_ = -1;
+    }
+  }
+
+  void Complete(IPCEnv* env, int pipe, int32_t batch_id) {
+    auto& ev = events_[pipe];
     for (int i = op_num_ - INTRABATCH_CON; i < op_num_; i++)  // join all three streams before the hand-off
-      LGCHECK(lg_event_synchronize(events_[i]));
+      LGCHECK(lg_event_synchronize(ev[i]));
     int32_t st = 0;
-    LGCHECK(lg_sampler_status(memorypool_->sampler, streams_[0], &st));
+    LGCHECK(lg_sampler_status(memorypool_->sampler, streams_[2], &st));  // sticky flag; stream 2 is idle
     if (st != 0) {
       std::fprintf(stderr, "batch %d on GPU %d overflowed its buffers (status %d)\n", batch_id, local_dev_id_, st);
       std::exit(EXIT_FAILURE);
     }
-    env->IPCPost(local_dev_id_, current_pipe_);
+    env->IPCPost(local_dev_id_, pipe);
     if (batch_id % 1000 == 0 && local_dev_id_ == 0) std::cout << "batch id: " << batch_id << "\n" << std::flush;
-    current_pipe_ = (current_pipe_ + 1) % interbatch_concurrency_;
-    memorypool_->SetCurrentPipe(current_pipe_);
   }
 
   void Finalize(RunnerParams* params) override {
     auto* env = (IPCEnv*)params->env;
+    LGCHECK(lg_set_device(local_dev_id_));
+    if (pending_pipe_ >= 0) Complete(env, pending_pipe_, pending_batch_);
+    pending_pipe_ = -1;
     env->IPCWait(local_dev_id_, (current_pipe_ + 1) % interbatch_concurrency_);  // server.cu:336
     LGCHECK(lg_set_device(local_dev_id_));
     lg_sampler_destroy(memorypool_->sampler);
-    for (auto& e : events_) lg_event_destroy(e);
+    for (auto& ev : events_)
+      for (auto& e : ev) lg_event_destroy(e);
     for (auto& s : streams_) lg_stream_destroy(s);
   }
 
@@ -248,7 +273,9 @@ class GPURunner : public Runner {
   MemoryPool* memorypool_ = nullptr;
   int current_pipe_ = 0, interbatch_concurrency_ = INTERBATCH_CON, local_dev_id_ = 0, mode_ = 0, op_num_ = 0;
   std::vector<lg_stream_t> streams_;
-  std::vector<lg_event_t> events_;
+  std::vector<std::vector<lg_event_t>> events_;  // [slot][op]
+  int pending_pipe_ = -1;
+  int32_t pending_batch_ = 0;
   std::vector<Operator*> ops_;
   std::vector<OpParams*> op_params_;
 };
