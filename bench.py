@@ -210,17 +210,42 @@ def run_ours(args):
     feature_rows = min(dp.num_ids, int(max_ids * 1.2) + 1)  # engine/server.cu:277
     del scratch, eh
     bufs = [dp.alloc_batch(feature_rows=feature_rows) for _ in range(2)]  # INTERBATCH_CON pipeline slots
+    dp.set_gather_fusion(args.fuse)
+    # additional batches in flight on the same GPU: own sampler scratch + buffers + stream, shared storage
+    runners = [(dp, bufs, torch.cuda.current_stream())]
+    for _ in range(args.inflight - 1):
+        d2 = DataPath(local, fanout, B, N, D, rank=rank, world=world)
+        d2.share_storage_from(dp)
+        d2.set_overlap(args.overlap)
+        d2.set_gather_fusion(args.fuse)
+        d2.set_gather_variant({"auto": capi.GATHER_AUTO, "ldg": capi.GATHER_LDG, "tma": capi.GATHER_TMA}[args.gather])
+        runners.append((d2, [d2.alloc_batch(feature_rows=feature_rows) for _ in range(2)], torch.cuda.Stream()))
+
+    def run_steps(first, count, tier=False):
+        """`count` batches round-robin over the in-flight runners; returns when all are enqueued and joined
+        into the current stream"""
+        cur = torch.cuda.current_stream()
+        for _, _, st in runners[1:]:
+            st.wait_stream(cur)
+        for s in range(count):
+            r, rb, st = runners[s % len(runners)]
+            with torch.cuda.stream(st):
+                r.run_once(params(first + s), rb[(s // len(runners)) % 2], tier=tier)
+        for r, rb, st in runners:
+            with torch.cuda.stream(st):
+                for b in rb:
+                    r.batch_wait(b)
+            if st is not cur:
+                cur.wait_stream(st)
 
     def params(step):
         return dp.params(d_train, d_lab, B, step % train_steps, seed=SEED, batch_id=step)
 
     # --- warm-up ---
-    for s in range(args.warmup):
-        dp.run_once(params(s), bufs[s % 2])
-    for b in bufs:
-        dp.batch_wait(b)
     torch.cuda.synchronize()
-    assert dp.status() == 0, "sampler overflow status"
+    run_steps(0, args.warmup)
+    torch.cuda.synchronize()
+    assert all(r.status() == 0 for r, _, _ in runners), "sampler overflow status"
 
     def barrier():
         if world > 1:
@@ -234,10 +259,7 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s in range(args.steps):
-        dp.run_once(params(args.warmup + s), bufs[s % 2], tier=True)
-    for b in bufs:
-        dp.batch_wait(b)  # pipelined mode: the last batches are complete before the clock stops
+    run_steps(args.warmup, args.steps, tier=True)  # all in-flight batches are complete before the clock stops
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -246,7 +268,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
-    tiers = dp.tier_rows.clone()
+    tiers = sum(r.tier_rows for r, _, _ in runners)
     if world > 1:
         dist.all_reduce(tiers)
     tiers = tiers.cpu().numpy().astype(np.int64)
@@ -256,36 +278,38 @@ def run_ours(args):
     # --- instrumented pass: same steps, CUDA events around each op (per-kernel durations) ---
     L = dp.L
     st = dp._stream()
-    names = ["batch_generate", "gather0"] + [x for h in range(1, H + 1) for x in (f"sample{h}", f"gather{h}")]
-    acc = {k: 0.0 for k in names}
     rows_total = 0
     n_inst = min(args.steps, 20)
+    acc = {}
     for s in range(n_inst):
         p = params(args.warmup + s)
         b = bufs[s % 2]
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ops = [("batch_generate", lambda: L.lg_batch_generate(dp.sampler, st, p.all_ids, p.all_labels, p.total_cap,
+                                                              p.batch_size, p.counter, C.byref(b.c)))]
+        pending = 0
+        for hop in range(0, H + 1):
+            if hop > 0:
+                ops.append((f"sample{hop}", lambda hop=hop: L.lg_random_sample(
+                    dp.sampler, st, C.byref(dp.topo), hop, p.rng_kind, p.rng_seed, p.batch_id, p.stream_id, C.byref(b.c), None)))
+            last = hop == H
+            if not last and (args.fuse == 2 or (args.fuse == 1 and hop == 0)):
+                continue
+            nm = f"gather{hop}" if pending == hop else f"gather{pending}-{hop}"  # rows of hops [pending, hop]
+            ops.append((nm, lambda hop=hop, pending=pending: L.lg_feature_cache_lookup_range(
+                dp.sampler, st, C.byref(dp.cache), 3 * hop + 1, pending, dp.local_part, C.byref(b.c), None)))
+            pending = hop + 1
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)]
         evs[0].record()
-        capi.check(L.lg_batch_generate(dp.sampler, st, p.all_ids, p.all_labels, p.total_cap, p.batch_size, p.counter,
-                                       C.byref(b.c)))
-        evs[1].record()
-        capi.check(L.lg_feature_cache_lookup(dp.sampler, st, C.byref(dp.cache), 1, dp.local_part, C.byref(b.c), None))
-        evs[2].record()
-        k = 2
-        for hop in range(1, H + 1):
-            capi.check(L.lg_random_sample(dp.sampler, st, C.byref(dp.topo), hop, p.rng_kind, p.rng_seed, p.batch_id,
-                                          p.stream_id, C.byref(b.c), None))
-            k += 1
-            evs[k].record()
-            capi.check(L.lg_feature_cache_lookup(dp.sampler, st, C.byref(dp.cache), 3 * hop + 1, dp.local_part,
-                                                 C.byref(b.c), None))
-            k += 1
-            evs[k].record()
+        for i, (nm, fn) in enumerate(ops):
+            capi.check(fn())
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        for i, nm in enumerate(names):
-            acc[nm] += evs[i].elapsed_time(evs[i + 1])
+        for i, (nm, _) in enumerate(ops):
+            acc[nm] = acc.get(nm, 0.0) + evs[i].elapsed_time(evs[i + 1])
         rows_total += int(b.node_counter[9 + H].item())
     breakdown = {k: v / n_inst for k, v in acc.items()}
     gather_ms = sum(v for k, v in breakdown.items() if k.startswith("gather"))
+    n_gather_launches = sum(1 for k in breakdown if k.startswith("gather"))
     rows_per_step = rows_total / n_inst
     alg_bytes = rows_per_step * (8 * D + 8)  # 4D read + 4D written + id + location
     achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
@@ -344,7 +368,7 @@ def run_ours(args):
             "config": {"workload": f"{shape['name']}-shaped synthetic graph fully HBM-cached (BASELINE.json configs[1])",
                        "num_nodes": N, "num_edges": E, "feature_dim": D, "fanout": fanout, "batch": B,
                        "scale": args.scale, "cache": f"Kc=1,Kg={world}: feature table interleaved by hotness rank over {world} GPU(s); topology replicated in HBM",
-                       "rng": "philox4x32-10", "gather_mover": args.gather, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
+                       "rng": "philox4x32-10", "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
                        "l2": "working set (topology + features + per-batch output, >1.5 GB) exceeds the 126 MB L2; every step samples different seeds"},
             "e2e": {"value": seeds / t_e2e, "unit": "seeds/s", "h2d_bytes_per_step": 2 * 4 * B, "d2h_bytes_per_step": 128,
                     "note": "host seed ids+labels in pinned memory -> lg_run_batch_host -> both counter arrays read back, "
@@ -354,14 +378,14 @@ def run_ours(args):
                                 "note": "same, plus ids/COO/features copied back to pinned host memory every step"},
             "gpu_launches": 0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "feature gather (3 launches per step)",
+                         "traffic": None, "peak_kind": peak_kind, "kernel": f"feature gather ({n_gather_launches} launch(es) per step)",
                          "algorithmic_bytes_per_step": alg_bytes, "rows_per_step": rows_per_step,
                          "gather_ms_per_step": gather_ms},
             "breakdown_ms": breakdown,
             "tier_rows": {"local": int(tiers[0]), "peer": int(tiers[1]), "host_or_backing": int(tiers[2])},
             "clocks": clk,
         }
-        out["gpu_launches"] = args.steps * (1 + (H + 1) + 2 * H)  # batch_generate + gathers + (sample, rank) per hop
+        out["gpu_launches"] = args.steps * (1 + n_gather_launches + 2 * H)  # batch_generate + gathers + (sample, rank) per hop
         tr = recorded_traffic()
         if tr:
             out["roofline"]["traffic"] = tr.get("traffic_bytes_per_step")
@@ -451,6 +475,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--presample", type=int, default=20, help="presampling batches used for the hotness ranking")
     ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--fuse", type=int, default=2, choices=[0, 1, 2],
+                    help="gather launches per batch: 0 one per lookup op, 1 seeds ride with hop 1, 2 single gather")
+    ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (own scratch + stream each)")
     ap.add_argument("--overlap", type=int, default=2, choices=[0, 1, 2],
                     help="0 one stream; 1 gathers overlap the next hop; 2 pipelined across the two batch slots")
     ap.add_argument("--cpu-steps", type=int, default=20)

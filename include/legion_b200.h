@@ -115,6 +115,10 @@ int lg_sampler_set_table_slots(lg_sampler* s, int64_t slots);
 int64_t lg_sampler_scratch_bytes(const lg_sampler* s);
 /* data mover used by lg_feature_cache_lookup: LG_GATHER_AUTO / LG_GATHER_LDG / LG_GATHER_TMA */
 int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant);
+/* how many gather launches lg_run_batch issues: 0 = one per lookup op (the reference's schedule);
+ * 1 (default) = the seeds' rows are moved together with hop 1's; 2 = one gather of all rows after the
+ * last hop.  Results (features, all counter slots) are identical in every mode. */
+int lg_sampler_set_gather_fusion(lg_sampler* s, int32_t mode);
 /* how lg_run_batch schedules the gathers: 0 = everything on the caller's stream; 1 (default) = gathers
  * on an internal side stream, overlapping the sampling of the next hop, joined before returning
  * (the reference's stream split, engine/server.cu:311-317); 2 = pipelined across batches like the
@@ -152,6 +156,12 @@ int lg_random_sample(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
 int lg_feature_cache_lookup(lg_sampler* s, lg_stream_t stream, const lg_feature_cache* cache,
                             int32_t op_id, int32_t local_part, const lg_batch* batch,
                             unsigned long long* tier_rows);
+
+/* same op, but one launch moves the rows of hops [first_hop, op_id/3] (fused gathers of lg_run_batch);
+ * the counter snapshot written is still the one of op_id */
+int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, const lg_feature_cache* cache,
+                                  int32_t op_id, int32_t first_hop, int32_t local_part,
+                                  const lg_batch* batch, unsigned long long* tier_rows);
 
 /* IOSubmit is a no-op in the reference (engine/operator_impl.cu:521-539); kept for API parity. */
 int lg_io_submit(lg_sampler* s, lg_stream_t stream, int32_t op_id, const lg_batch* batch);

@@ -52,12 +52,15 @@ _PROTOS = {
     "lg_sampler_scratch_bytes": (C.c_int64, [vp]),
     "lg_sampler_set_gather_variant": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_overlap": (C.c_int, [vp, C.c_int32]),
+    "lg_sampler_set_gather_fusion": (C.c_int, [vp, C.c_int32]),
     "lg_batch_wait": (C.c_int, [vp, vp, C.POINTER(Batch)]),
     "lg_sampler_status": (C.c_int, [vp, vp, C.POINTER(C.c_int32)]),
     "lg_batch_generate": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Batch)]),
     "lg_random_sample": (C.c_int, [vp, vp, C.POINTER(Topology), C.c_int32, C.c_int32, C.c_uint64, C.c_uint32,
                                    C.c_uint32, C.POINTER(Batch), vp]),
     "lg_feature_cache_lookup": (C.c_int, [vp, vp, C.POINTER(FeatureCache), C.c_int32, C.c_int32, C.POINTER(Batch), vp]),
+    "lg_feature_cache_lookup_range": (C.c_int, [vp, vp, C.POINTER(FeatureCache), C.c_int32, C.c_int32, C.c_int32,
+                                              C.POINTER(Batch), vp]),
     "lg_io_submit": (C.c_int, [vp, vp, C.c_int32, C.POINTER(Batch)]),
     "lg_io_complete": (C.c_int, [vp, vp, C.c_int32, C.POINTER(Batch), vp, vp]),
     "lg_run_batch": (C.c_int, [vp, vp, C.POINTER(Topology), C.POINTER(FeatureCache), C.POINTER(BatchParams),

@@ -26,6 +26,7 @@ struct GatherArgs {
   int64_t off, cnt;    // used when nc == null
   int64_t dst_rows;    // capacity of dst in rows
   int32_t hop;         // op_id / 3
+  int32_t hop_lo;      // first hop whose rows this launch moves (== hop unless the batch's gathers are fused)
   int32_t op_slot;     // op_id % 3 (snapshot slot, engine/operator_impl.cu:83-85)
   int32_t local_part;
   u64* tier;           // [3] local / peer / miss rows, may be null
@@ -39,9 +40,10 @@ __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int
     // (engine/operator_impl.cu:65-81) but immutable afterwards, so a later hop may already run.
     int32_t lo = a.hop == 0 ? 0 : a.nc[LG_INTRABATCH_CON * 3 + a.hop - 1];
     int32_t hi = a.nc[LG_INTRABATCH_CON * 3 + a.hop];
-    *off = lo;
-    *cnt = hi - lo;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the op's counter_update (:83-85)
+    int32_t first = a.hop_lo == 0 ? 0 : a.nc[LG_INTRABATCH_CON * 3 + a.hop_lo - 1];
+    *off = first;
+    *cnt = hi - first;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the op's counter_update (:83-85): snapshot of hop `hop`
       a.nc[a.op_slot * 2] = lo;
       a.nc[a.op_slot * 2 + 1] = hi - lo;
     }
@@ -418,6 +420,13 @@ int check_cache(const lg_feature_cache* c) {
 extern "C" int lg_feature_cache_lookup(lg_sampler* s, lg_stream_t stream, const lg_feature_cache* cache,
                                        int32_t op_id, int32_t local_part, const lg_batch* b,
                                        unsigned long long* tier_rows) {
+  return lg_feature_cache_lookup_range(s, stream, cache, op_id, op_id / LG_INTRABATCH_CON, local_part, b, tier_rows);
+}
+
+// rows of hops [first_hop, op_id/3] in one launch (fused gathers of lg_run_batch)
+extern "C" int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, const lg_feature_cache* cache, int32_t op_id,
+                                  int32_t first_hop, int32_t local_part, const lg_batch* b,
+                                  unsigned long long* tier_rows) {
   LG_REQUIRE(s && b, "lg_feature_cache_lookup: null argument");
   int rc = check_cache(cache);
   if (rc) return rc;
@@ -432,13 +441,17 @@ extern "C" int lg_feature_cache_lookup(lg_sampler* s, lg_stream_t stream, const 
   a.cnt = 0;
   a.dst_rows = b->feature_rows;
   a.hop = op_id / LG_INTRABATCH_CON;
+  LG_REQUIRE(first_hop >= 0 && first_hop <= op_id / LG_INTRABATCH_CON, "lg_feature_cache_lookup_range: first_hop %d", first_hop);
+  a.hop_lo = first_hop;
   a.op_slot = op_id % LG_INTRABATCH_CON;
   a.local_part = local_part;
   a.tier = (u64*)tier_rows;
   a.status = s->status;
   a.hot_rows = 0;
   LG_REQUIRE(a.hop <= s->n_hops, "lg_feature_cache_lookup: op_id %d beyond %d hops", op_id, s->n_hops);
-  return launch_gather((cudaStream_t)stream, a, s->gather_variant, s->slots_per_hop[a.hop]);
+  int64_t max_rows = 0;
+  for (int h = first_hop; h <= a.hop; h++) max_rows += s->slots_per_hop[h];
+  return launch_gather((cudaStream_t)stream, a, s->gather_variant, max_rows);
 }
 
 extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache, const int32_t* ids, int64_t n,
@@ -458,6 +471,7 @@ extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache,
   a.cnt = n;
   a.dst_rows = n;
   a.hop = 0;
+  a.hop_lo = 0;
   a.op_slot = 0;
   a.local_part = local_part;
   a.tier = (u64*)tier_rows;

@@ -455,6 +455,7 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   for (int h = 0; h <= LG_MAX_HOPS; h++) LG_CUDA(cudaEventCreateWithFlags(&s->ev_fork[h], cudaEventDisableTiming));
   LG_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   s->overlap = 1;
+  s->fuse_gathers = 1;
   int rc = sampler_alloc_table(s, next_pow2(s->num_ids + s->num_ids / 2));
   if (rc) return rc;
   *out = s;
@@ -491,6 +492,13 @@ extern "C" int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant) {
   LG_REQUIRE(s, "null sampler");
   LG_REQUIRE(variant >= LG_GATHER_AUTO && variant <= LG_GATHER_TMA, "gather variant %d", variant);
   s->gather_variant = variant;
+  return 0;
+}
+
+extern "C" int lg_sampler_set_gather_fusion(lg_sampler* s, int32_t mode) {
+  LG_REQUIRE(s, "null sampler");
+  LG_REQUIRE(mode >= 0 && mode <= 2, "gather fusion mode %d", mode);
+  s->fuse_gathers = mode;
   return 0;
 }
 
@@ -660,18 +668,25 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
   }
   int rc = lg_batch_generate(s, stream, p->all_ids, p->all_labels, p->total_cap, p->batch_size, p->counter, b);
   if (rc) return rc;
+  int first_pending = 0;  // first hop whose rows have not been gathered yet
   for (int hop = 0; hop <= s->n_hops; hop++) {
     if (hop > 0) {
       rc = lg_random_sample(s, stream, topo, hop, p->rng_kind, p->rng_seed, p->batch_id, p->stream_id, b, nullptr);
       if (rc) return rc;
     }
     if (!cache) continue;
+    // gather fusion: the final counters equal the reference's (the last lookup op's snapshot wins);
+    // only the NUMBER of gather launches changes
+    const bool last = (hop == s->n_hops);
+    if (!last && (s->fuse_gathers == 2 || (s->fuse_gathers == 1 && hop == 0))) continue;
     if (fork) {
       LG_CUDA(cudaEventRecord(s->ev_fork[hop], main_st));
       LG_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork[hop], 0));
     }
-    rc = lg_feature_cache_lookup(s, gst, cache, hop * LG_INTRABATCH_CON + 1, p->local_part, b, tier_rows);
+    rc = lg_feature_cache_lookup_range(s, gst, cache, hop * LG_INTRABATCH_CON + 1, first_pending, p->local_part, b,
+                                       tier_rows);
     if (rc) return rc;
+    first_pending = hop + 1;
   }
   if (pipelined) {  // no join: the next batch is sampled while this batch's last gather streams
     LG_CUDA(cudaEventRecord(ev_done, s->side));

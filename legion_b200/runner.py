@@ -333,6 +333,18 @@ class DataPath:
         """0 one stream, 1 gathers overlap the next hop (joined per batch), 2 pipelined across batches"""
         check(self.L.lg_sampler_set_overlap(self.sampler, int(mode)))
 
+    def set_gather_fusion(self, mode):
+        """0 one gather per op, 1 seeds ride with hop 1, 2 single gather per batch"""
+        check(self.L.lg_sampler_set_gather_fusion(self.sampler, int(mode)))
+
+    def share_storage_from(self, other):
+        """a second in-flight runner on the same GPU: same topology / cache descriptors, own scratch"""
+        self._full, self._backing = other._full, other._backing
+        self.topo, self.cache = other.topo, other.cache
+        self.topo_directory, self.feat_directory = getattr(other, "topo_directory", None), getattr(other, "feat_directory", None)
+        self.local_part = other.local_part
+        self._keep.append(other)
+
     def batch_wait(self, buf):
         check(self.L.lg_batch_wait(self.sampler, self._stream(), C.byref(buf.c)))
 

@@ -245,8 +245,9 @@ def test_distribution_fanout_and_uniformity(oracle):
     assert abs(inc_dgl.mean() - c / degv) < 1e-9 and np.abs(inc_dgl - c / degv).max() < 0.05
 
 
+@pytest.mark.parametrize("fuse", [0, 1, 2])
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_stream_schedules_give_identical_batches(oracle, mode):
+def test_stream_schedules_give_identical_batches(oracle, mode, fuse):
     """one stream / gather overlapping the next hop / pipelined over two buffer slots: same bits"""
     indptr, indices = small_graph(3000, 14.0, 400)
     N = len(indptr) - 1
@@ -255,6 +256,7 @@ def test_stream_schedules_give_identical_batches(oracle, mode):
     fanout, B = [10, 5], 128
     rig = Rig(indptr, indices, feat, fanout, B)
     rig.dp.set_overlap(mode)
+    rig.dp.set_gather_fusion(fuse)
     d_ids, d_lab = rig.sets(ids, labels)
     bufs = [rig.dp.alloc_batch(), rig.dp.alloc_batch()]
     orc = oracle.Oracle(indptr, indices, fanout, B)
@@ -271,3 +273,37 @@ def test_stream_schedules_give_identical_batches(oracle, mode):
     torch.cuda.synchronize()
     want = orc.run_batch(ids, labels, B, n_batches - 1, seed=17, batch_id=n_batches - 1)
     assert_batch_equal(bufs[(n_batches - 1) % 2].to_host(2), want, 2, feat)
+
+
+def test_two_runners_in_flight_on_one_gpu(oracle):
+    """two sampler handles on two streams sharing the storage descriptors (bench --inflight 2)"""
+    from legion_b200.runner import DataPath
+    indptr, indices = small_graph(3000, 14.0, 400)
+    N = len(indptr) - 1
+    feat = _feat(N, 100)
+    ids, labels = make_sets(N)
+    fanout, B = [10, 5], 128
+    rig = Rig(indptr, indices, feat, fanout, B)
+    hot = torch.from_numpy(np.bincount(indices, minlength=N).astype(np.int64)).to(rig.dev)
+    order, _ = rig.dp.rank_hotness(hot)
+    rig.dp.build_feature_cache(order, cap=1000)
+    d2 = DataPath(0, fanout, B, N, 100)
+    d2.share_storage_from(rig.dp)
+    runners = [(rig.dp, rig.dp.alloc_batch(), torch.cuda.current_stream()), (d2, d2.alloc_batch(), torch.cuda.Stream())]
+    for r, _, _ in runners:
+        r.set_overlap(2)
+        r.set_gather_fusion(2)
+    d_ids, d_lab = rig.sets(ids, labels)
+    torch.cuda.synchronize()
+    orc = oracle.Oracle(indptr, indices, fanout, B)
+    for rnd in range(3):
+        for k, (r, buf, st) in enumerate(runners):
+            with torch.cuda.stream(st):
+                r.run_once(r.params(d_ids, d_lab, B, 2 * rnd + k, seed=3, batch_id=2 * rnd + k), buf)
+        for k, (r, buf, st) in enumerate(runners):
+            with torch.cuda.stream(st):
+                r.batch_wait(buf)
+            st.synchronize()
+            want = orc.run_batch(ids, labels, B, 2 * rnd + k, seed=3, batch_id=2 * rnd + k)
+            assert_batch_equal(buf.to_host(2), want, 2, feat)
+    d2.close()
