@@ -28,9 +28,10 @@ sys.path.insert(0, ROOT)
 
 SEED = 0x1E910
 WORKLOADS = {
-    # name: (shape key, fanout, batch, dmax)
-    "products": ("products", [25, 10], 8000, 20000),
-    "products-small": ("products", [25, 10], 8000, 20000),  # scaled by --scale for smoke runs
+    # name: (shape key, fanout, batch, dmax, materialise the [N x D] matrix in vertex order?)
+    "products": ("products", [25, 10], 8000, 20000, True),     # BASELINE.json configs[1] (default)
+    "paper100m": ("paper100m", [25, 10], 8000, 20000, False),  # configs[2] shape
+    "ukunion": ("ukunion", [25, 10], 8000, 20000, False),      # configs[3] shape: the metric's named graph
 }
 
 
@@ -114,12 +115,12 @@ def recorded_traffic():
 # ----------------------------------------------------------------------------------------------
 def shape_of(args):
     from legion_b200 import synth
-    key, fanout, batch, dmax = WORKLOADS[args.workload]
+    key, fanout, batch, dmax, dense = WORKLOADS[args.workload]
     n, e, d, classes = synth.SHAPES[key]
     n = max(1000, int(n * args.scale))
     e_target = int(e * args.scale)
     return dict(name=key, N=n, E_target=e_target, D=d, classes=classes, fanout=fanout, batch=args.batch or batch,
-                dmax=dmax, dmin=synth.dmin_for(n, e_target))
+                dmax=dmax, dmin=synth.dmin_for(n, e_target), dense=dense)
 
 
 def device_dataset(shape, device):
@@ -135,8 +136,10 @@ def device_dataset(shape, device):
     E = int(ip[N].item())
     ix = torch.empty(E, dtype=torch.int32, device=dev)
     capi.check(L.lg_synth_indices(st, N, ip.data_ptr(), SEED, ix.data_ptr()))
-    feat = torch.empty((N, D), dtype=torch.float32, device=dev)
-    capi.check(L.lg_synth_features(st, 0, N, D, SEED, feat.data_ptr()))
+    feat = None
+    if shape["dense"]:
+        feat = torch.empty((N, D), dtype=torch.float32, device=dev)
+        capi.check(L.lg_synth_features(st, 0, N, D, SEED, feat.data_ptr()))
     lab = torch.empty(N, dtype=torch.int32, device=dev)
     capi.check(L.lg_synth_labels(st, N, shape["classes"], lab.data_ptr()))
     torch.cuda.synchronize()
@@ -144,8 +147,15 @@ def device_dataset(shape, device):
 
 
 def train_split(shape, world):
+    """random 10 % of the vertices (dataset/gen_sets.py:62-67), split by id % gpus (storage_management.cu:175-179)"""
     from legion_b200 import synth
-    tr, _, _ = synth.split_sets(shape["N"], SEED)
+    if shape["N"] <= 20_000_000:
+        tr, _, _ = synth.split_sets(shape["N"], SEED)
+    else:  # paper-scale: draw the permutation on the device
+        import torch
+        g = torch.Generator(device="cuda")
+        g.manual_seed(SEED)
+        tr = torch.randperm(shape["N"], device="cuda", generator=g)[: shape["N"] // 10].to(torch.int32).cpu().numpy()
     return synth.partition_ids(tr, world)
 
 
@@ -186,7 +196,8 @@ def run_ours(args):
 
     dp = DataPath(local, fanout, B, N, D, rank=rank, world=world)
     dp.set_full_graph(ip.data_ptr(), ix.data_ptr(), keep=[ip, ix])  # topology replicated in each GPU's HBM
-    dp.set_backing_features(feat.data_ptr(), keep=[feat])
+    if feat is not None:
+        dp.set_backing_features(feat.data_ptr(), keep=[feat])
     dp.set_overlap(args.overlap)
     dp.set_gather_variant({"auto": capi.GATHER_AUTO, "ldg": capi.GATHER_LDG, "tma": capi.GATHER_TMA}[args.gather])
 
@@ -205,10 +216,14 @@ def run_ours(args):
     order, _ = dp.rank_hotness(nh)
     kg = world
     cap = (N + kg - 1) // kg  # whole table cached across the clique
-    dp.build_feature_cache(order, cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
+    if feat is not None:
+        dp.build_feature_cache(order, cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
+    else:  # paper-scale shapes: shards generated in place, no [N x D] matrix in vertex order anywhere
+        dp.build_feature_cache_synth(order, cap, SEED, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
     max_ids = int(mx.item())
     feature_rows = min(dp.num_ids, int(max_ids * 1.2) + 1)  # engine/server.cu:277
-    del scratch, eh
+    del scratch, eh, nh
+    torch.cuda.empty_cache()
     bufs = [dp.alloc_batch(feature_rows=feature_rows) for _ in range(2)]  # INTERBATCH_CON pipeline slots
     dp.set_gather_fusion(args.fuse)
     # additional batches in flight on the same GPU: own sampler scratch + buffers + stream, shared storage
@@ -245,6 +260,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     run_steps(0, args.warmup)
     torch.cuda.synchronize()
+    # self-check: the rows gathered for the last warm-up batch equal the feature function of their ids, bit for bit
+    r0, rb0, _ = runners[(args.warmup - 1) % len(runners)]
+    b0 = rb0[((args.warmup - 1) // len(runners)) % 2]
+    n0 = int(b0.node_counter[9 + H].item())
+    chk = torch.empty((n0, D), dtype=torch.float32, device=dev)
+    capi.check(dp.L.lg_synth_feature_rows(dp._stream(), b0.ids.data_ptr(), n0, D, SEED, chk.data_ptr()))
+    torch.cuda.synchronize()
+    features_ok = bool(torch.equal(chk.view(torch.int32), b0.features[:n0].view(torch.int32)))
+    assert features_ok, "gathered features differ from the feature function"
+    del chk
     assert all(r.status() == 0 for r, _, _ in runners), "sampler overflow status"
 
     def barrier():
@@ -318,6 +343,7 @@ def run_ours(args):
     # --- end-to-end: host seeds in (pinned), counters out, every step synchronised ---
     h_ids = torch.from_numpy(my_train[: B * train_steps].copy()).pin_memory()
     h_lab = lab[torch.from_numpy(my_train[: B * train_steps].astype(np.int64)).to(dev)].cpu().pin_memory()
+    pin = pin_feat = None
     h_nc, h_ec = np.zeros(16, np.int32), np.zeros(16, np.int32)
 
     def e2e_step(s):
@@ -365,7 +391,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 ids / fp32 rows moved bit-exact",
             "data": "synthetic",
-            "config": {"workload": f"{shape['name']}-shaped synthetic graph fully HBM-cached (BASELINE.json configs[1])",
+            "config": {"workload": f"{shape['name']}-shaped synthetic graph fully HBM-cached (BASELINE.json " + {"products": "configs[1]", "paper100m": "configs[2] shape", "ukunion": "configs[3] shape, 128-d"}[shape["name"]] + ")",
                        "num_nodes": N, "num_edges": E, "feature_dim": D, "fanout": fanout, "batch": B,
                        "scale": args.scale, "cache": f"Kc=1,Kg={world}: feature table interleaved by hotness rank over {world} GPU(s); topology replicated in HBM",
                        "rng": "philox4x32-10", "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
@@ -381,7 +407,7 @@ def run_ours(args):
                          "traffic": None, "peak_kind": peak_kind, "kernel": f"feature gather ({n_gather_launches} launch(es) per step)",
                          "algorithmic_bytes_per_step": alg_bytes, "rows_per_step": rows_per_step,
                          "gather_ms_per_step": gather_ms},
-            "breakdown_ms": breakdown,
+            "breakdown_ms": breakdown, "features_bit_exact_selfcheck": features_ok,
             "tier_rows": {"local": int(tiers[0]), "peer": int(tiers[1]), "host_or_backing": int(tiers[2])},
             "clocks": clk,
         }
@@ -391,7 +417,7 @@ def run_ours(args):
             out["roofline"]["traffic"] = tr.get("traffic_bytes_per_step")
             out["roofline"]["traffic_source"] = tr.get("source")
     # --- CPU baseline beside it (rank 0, N=1 only) ---
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and feat is not None:
         out["cpu_baseline"] = cpu_arm(shape, ip.cpu().numpy(), ix.cpu().numpy(), feat.cpu().numpy(), my_train, steps=args.cpu_steps,
                                       warmup=1)["cpu_baseline"]
     if world > 1:

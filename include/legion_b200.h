@@ -81,7 +81,8 @@ typedef struct lg_feature_cache {
   int32_t reserved;
   int64_t num_nodes;
   const float* shard[LG_MAX_DEVICE];
-  const float* backing;     /* full [num_nodes x dim] matrix: host UVA pointer or HBM */
+  const float* backing;     /* full [num_nodes x dim] matrix: host UVA pointer or HBM; may be NULL when the
+                               directory covers every vertex (a miss then sets status 3) */
   const int32_t* directory; /* NULL = every row misses */
 } lg_feature_cache;
 
@@ -127,7 +128,7 @@ int lg_sampler_set_gather_fusion(lg_sampler* s, int32_t mode);
 int lg_sampler_set_overlap(lg_sampler* s, int32_t mode);
 /* make `stream` wait until the batch last produced into `batch` is complete (mode 2; no-op otherwise) */
 int lg_batch_wait(lg_sampler* s, lg_stream_t stream, const lg_batch* batch);
-/* sticky overflow status (0 ok, 1 ids overflow, 2 features buffer too small — the reference
+/* sticky overflow status (0 ok, 1 ids overflow, 3 cache miss without a backing matrix, 2 features buffer too small — the reference
  * sizes it 1.2 x presampled max without a bound check, engine/server.cu:277).  Synchronises. */
 int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);
 

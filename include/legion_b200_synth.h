@@ -27,6 +27,14 @@ int lg_synth_indices(void* stream, int64_t num_nodes, const int64_t* indptr, uin
 int lg_synth_features(void* stream, int64_t row0, int64_t rows, int32_t dim, uint64_t seed,
                       float* out);
 int lg_synth_labels(void* stream, int64_t num_nodes, int32_t classes, int32_t* labels);
+/* out[r,:] = feat(ids[r], :) for r < n; rows with ids[r] < 0 are zero-filled.  Used to check gathered rows at
+ * scales where the feature matrix is never materialised in vertex order. */
+int lg_synth_feature_rows(void* stream, const int32_t* ids, int64_t n, int32_t dim, uint64_t seed,
+                          float* out);
+/* a cache shard generated in place: shard[r,:] = feat(order[r*kg + j], :) (FeatFillUp, cache/cache_impl.cuh:183-188,
+ * without a backing matrix); ranks >= num_nodes are zero-filled */
+int lg_synth_feature_shard(void* stream, const int32_t* order, int64_t cap, int32_t kg, int32_t j,
+                           int32_t dim, int64_t num_nodes, uint64_t seed, float* shard);
 #ifdef __cplusplus
 }
 #endif

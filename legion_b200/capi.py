@@ -107,6 +107,8 @@ _PROTOS = {
     "lg_synth_indices": (C.c_int, [vp, C.c_int64, vp, C.c_uint64, vp]),
     "lg_synth_features": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, vp]),
     "lg_synth_labels": (C.c_int, [vp, C.c_int64, C.c_int32, vp]),
+    "lg_synth_feature_rows": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_uint64, vp]),
+    "lg_synth_feature_shard": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, vp]),
 }
 
 _lib = None

@@ -62,6 +62,10 @@ __device__ __forceinline__ const float* locate(const GatherArgs& a, int32_t id, 
   if (a.cache.directory && id < a.cache.num_nodes) gidx = a.cache.directory[id];
   if (gidx < 0) {  // miss -> backing matrix (cache_impl.cuh:262-266)
     *t = 2;
+    if (!a.cache.backing) {  // fully-cached deployment without a backing matrix: a miss is an error
+      *a.status = 3;
+      return nullptr;
+    }
     return a.cache.backing + (int64_t)(id % a.cache.num_nodes) * a.cache.dim;
   }
   int32_t didx = gidx / a.cache.shard_rows;  // cache_impl.cuh:259-260
@@ -272,6 +276,10 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
     if (id < 0) return nullptr;  // -1 padding / out of range rows are skipped (cache_impl.cuh:263-264)
     if (gidx < 0) {              // miss -> backing matrix (cache_impl.cuh:262-266)
       t2++;
+      if (!a.cache.backing) {
+        *a.status = 3;
+        return nullptr;
+      }
       return a.cache.backing + (int64_t)(id % a.cache.num_nodes) * a.cache.dim;
     }
     const int32_t didx = gidx / a.cache.shard_rows;  // cache_impl.cuh:259-260
@@ -409,7 +417,7 @@ int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) 
 int check_cache(const lg_feature_cache* c) {
   LG_REQUIRE(c, "feature cache descriptor is null");
   LG_REQUIRE(c->dim > 0, "feature cache: dim %d", c->dim);
-  LG_REQUIRE(c->backing, "feature cache: backing matrix is null");
+  LG_REQUIRE(c->backing || c->directory, "feature cache: neither a backing matrix nor a directory");
   LG_REQUIRE(c->n_parts >= 0 && c->n_parts <= LG_MAX_DEVICE, "feature cache: n_parts %d", c->n_parts);
   LG_REQUIRE(!c->directory || c->shard_rows > 0, "feature cache: directory without shard_rows");
   return 0;

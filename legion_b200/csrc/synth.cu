@@ -49,6 +49,21 @@ __global__ void features_kernel(int64_t row0, int64_t rows, int32_t dim, u64 see
     out[i] = __uint_as_float(bits);
   }
 }
+// rows addressed through an id list: out[r, c] = feat(idmap(r), c)
+__global__ void feature_rows_kernel(const int32_t* __restrict__ ids, int64_t stride, int64_t offset, int64_t id_count,
+                                    int64_t rows, int32_t dim, u64 seed, float* __restrict__ out) {
+  const u64 s3 = seed ^ 0xFEA7FEA7FEA7FEA7ull;
+  const int64_t total = rows * dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dim;
+    const int32_t c = (int32_t)(i - r * dim);
+    const int64_t k = r * stride + offset;
+    const int32_t v = (k < id_count) ? ids[k] : -1;
+    uint32_t bits = 0;
+    if (v >= 0) bits = (uint32_t)hash2(s3, (u64)((int64_t)v * dim + c)) & 0xBFFFFFFFu;
+    out[i] = __uint_as_float(bits);
+  }
+}
 __global__ void labels_kernel(int64_t n, int32_t classes, int32_t* __restrict__ out) {
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
     out[v] = (int32_t)(v % classes);
@@ -91,6 +106,20 @@ extern "C" int lg_synth_features(void* stream, int64_t row0, int64_t rows, int32
 extern "C" int lg_synth_labels(void* stream, int64_t n, int32_t classes, int32_t* labels) {
   LG_REQUIRE(labels && n > 0 && classes > 0, "lg_synth_labels: bad argument");
   labels_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, classes, labels);
+  LG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int lg_synth_feature_rows(void* stream, const int32_t* ids, int64_t n, int32_t dim, uint64_t seed, float* out) {
+  LG_REQUIRE(ids && out && n >= 0 && dim > 0, "lg_synth_feature_rows: bad argument");
+  if (n == 0) return 0;
+  feature_rows_kernel<<<grid_for(n * dim), 256, 0, (cudaStream_t)stream>>>(ids, 1, 0, n, n, dim, seed, out);
+  LG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int lg_synth_feature_shard(void* stream, const int32_t* order, int64_t cap, int32_t kg, int32_t j, int32_t dim,
+                                      int64_t num_nodes, uint64_t seed, float* shard) {
+  LG_REQUIRE(order && shard && cap > 0 && kg > 0 && j >= 0 && j < kg && dim > 0, "lg_synth_feature_shard: bad argument");
+  feature_rows_kernel<<<grid_for(cap * dim), 256, 0, (cudaStream_t)stream>>>(order, kg, j, num_nodes, cap, dim, seed, shard);
   LG_LAUNCH_OK();
   return 0;
 }

@@ -202,7 +202,7 @@ class DataPath:
         c.num_nodes = self.N
         for i, p in enumerate(shard_ptrs):
             c.shard[i] = int(p)
-        c.backing = self._backing
+        c.backing = self._backing if self._backing else None
         c.directory = directory.data_ptr() if directory is not None else None
         self.cache = c
         self.feat_directory = directory
@@ -239,6 +239,28 @@ class DataPath:
         if kg > 1:
             shard_ptrs = self._exchange(raw, cap * self.dim * 4, kg, j, dist)
         self.local_part = j
+        self._set_cache(shard_ptrs, directory, cap)
+        self.feat_shard = raw
+        return directory
+
+    def build_feature_cache_synth(self, order, cap, seed, kg=1, j=0, dist=None):
+        """as build_feature_cache, but the shard is generated in place from the synthetic feature function
+        (include/legion_b200_synth.h): no [N x D] backing matrix exists anywhere (paper-scale shapes)"""
+        st = self._stream()
+        dev = f"cuda:{self.device}"
+        directory = torch.empty(self.N, dtype=I32, device=dev)
+        check(self.L.lg_fill_i32(st, _ptr(directory), capi.CACHEMISS_FLAG, self.N))
+        check(self.L.lg_place_features(st, _ptr(order), cap, kg, self.N, _ptr(directory)))
+        raw = RawDeviceBuffer(cap * self.dim * 4, self.device)
+        check(self.L.lg_synth_feature_shard(st, _ptr(order), cap, kg, j, self.dim, self.N, seed, C.c_void_p(raw.ptr)))
+        torch.cuda.current_stream().synchronize()
+        shard_ptrs = [0] * kg
+        shard_ptrs[j] = raw.ptr
+        self._keep.append(raw)
+        if kg > 1:
+            shard_ptrs = self._exchange(raw, cap * self.dim * 4, kg, j, dist)
+        self.local_part = j
+        self._backing = 0
         self._set_cache(shard_ptrs, directory, cap)
         self.feat_shard = raw
         return directory
