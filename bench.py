@@ -176,6 +176,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     capi.load()  # fails loudly if the CUDA library is missing
 
@@ -211,10 +212,20 @@ def run_ours(args):
         dp.run_presc(dp.params(d_train, d_lab, B, it, seed=SEED, batch_id=it), scratch, eh, nh, mx)
     torch.cuda.synchronize()
     if world > 1:
-        dist.all_reduce(nh)  # init-time 8-way sum of hotness (cache/cache.cu:408-411); not on the serving path
+        dist.all_reduce(nh)  # init-time sum of hotness over the GPUs (cache/cache.cu:408-411); not on the serving path
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     order, _ = dp.rank_hotness(nh)
-    kg = world
+    # cache aggregation (Legion's cache_agg_mode: Kg GPUs share one partitioned cache, Kc = world/Kg replicas).
+    # auto = the smallest power of two whose per-GPU shard fits the cache budget: on 180 GB parts the named
+    # shapes replicate (Kg=1, no NVLink traffic); --kg N forces the NVSwitch-partitioned layout.
+    table_bytes = N * D * 4
+    if args.kg > 0:
+        kg = args.kg
+    else:
+        kg = 1
+        while kg < world and table_bytes / kg > args.cache_gb * 1e9:
+            kg *= 2
+    assert world % kg == 0, "world size must be a multiple of Kg"
     cap = (N + kg - 1) // kg  # whole table cached across the clique
     if feat is not None:
         dp.build_feature_cache(order, cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
@@ -257,6 +268,9 @@ def run_ours(args):
         return dp.params(d_train, d_lab, B, step % train_steps, seed=SEED, batch_id=step)
 
     # --- warm-up ---
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     torch.cuda.synchronize()
     run_steps(0, args.warmup)
     torch.cuda.synchronize()
@@ -278,9 +292,6 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # --- timed region: exactly K steps, device-timed, max over ranks ---
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -288,7 +299,6 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -332,6 +342,7 @@ def run_ours(args):
         for i, (nm, _) in enumerate(ops):
             acc[nm] = acc.get(nm, 0.0) + evs[i].elapsed_time(evs[i + 1])
         rows_total += int(b.node_counter[9 + H].item())
+    clk = clocks.stop() if rank == 0 else None  # sampled from warm-up through the timed and instrumented passes
     breakdown = {k: v / n_inst for k, v in acc.items()}
     gather_ms = sum(v for k, v in breakdown.items() if k.startswith("gather"))
     n_gather_launches = sum(1 for k in breakdown if k.startswith("gather"))
@@ -339,6 +350,15 @@ def run_ours(args):
     alg_bytes = rows_per_step * (8 * D + 8)  # 4D read + 4D written + id + location
     achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
     peak, peak_kind = measured_peak()
+    # roofline for the measured hit mix: per row, HBM moves 4D(l+p)+4D (own local reads + reads served
+    # to peers + own writes), NVLink-in 4D*p, PCIe 4D*h; t_roof = max over the three links
+    tsum = max(int(tiers.sum()), 1)
+    fl, fp, fh = (float(x) / tsum for x in tiers)
+    nvl_bw, pcie_bw = 770.0, 55.0  # GB/s: measured peer-copy figure of this pool (B200_PROFILING.md); PCIe Gen5 x16 practical
+    t_parts = {"hbm": rows_per_step * (4 * D * (fl + fp) + 4 * D + 8) / (peak * 1e9),
+               "nvlink": rows_per_step * 4 * D * fp / (nvl_bw * 1e9), "pcie": rows_per_step * 4 * D * fh / (pcie_bw * 1e9)}
+    mix_bound = max(t_parts, key=t_parts.get)
+    mix_frac = t_parts[mix_bound] / (gather_ms * 1e-3)
 
     # --- end-to-end: host seeds in (pinned), counters out, every step synchronised ---
     h_ids = torch.from_numpy(my_train[: B * train_steps].copy()).pin_memory()
@@ -393,7 +413,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"{shape['name']}-shaped synthetic graph fully HBM-cached (BASELINE.json " + {"products": "configs[1]", "paper100m": "configs[2] shape", "ukunion": "configs[3] shape, 128-d"}[shape["name"]] + ")",
                        "num_nodes": N, "num_edges": E, "feature_dim": D, "fanout": fanout, "batch": B,
-                       "scale": args.scale, "cache": f"Kc=1,Kg={world}: feature table interleaved by hotness rank over {world} GPU(s); topology replicated in HBM",
+                       "scale": args.scale, "cache": f"Kc={world // kg},Kg={kg}: feature table interleaved by hotness rank over {kg} GPU(s) per clique; topology replicated in HBM",
                        "rng": "philox4x32-10", "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
                        "l2": "working set (topology + features + per-batch output, >1.5 GB) exceeds the 126 MB L2; every step samples different seeds"},
             "e2e": {"value": seeds / t_e2e, "unit": "seeds/s", "h2d_bytes_per_step": 2 * 4 * B, "d2h_bytes_per_step": 128,
@@ -406,7 +426,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": peak_kind, "kernel": f"feature gather ({n_gather_launches} launch(es) per step)",
                          "algorithmic_bytes_per_step": alg_bytes, "rows_per_step": rows_per_step,
-                         "gather_ms_per_step": gather_ms},
+                         "gather_ms_per_step": gather_ms,
+                         "hit_mix": {"local": fl, "peer": fp, "host": fh, "bound": mix_bound, "frac_of_mix_roofline": mix_frac,
+                                     "nvlink_GBps_assumed": nvl_bw, "pcie_GBps_assumed": pcie_bw}},
             "breakdown_ms": breakdown, "features_bit_exact_selfcheck": features_ok,
             "tier_rows": {"local": int(tiers[0]), "peer": int(tiers[1]), "host_or_backing": int(tiers[2])},
             "clocks": clk,
@@ -493,7 +515,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
@@ -503,6 +525,8 @@ def main():
     ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "tma"])
     ap.add_argument("--fuse", type=int, default=2, choices=[0, 1, 2],
                     help="gather launches per batch: 0 one per lookup op, 1 seeds ride with hop 1, 2 single gather")
+    ap.add_argument("--kg", type=int, default=0, help="GPUs sharing one partitioned cache (0 = auto by capacity)")
+    ap.add_argument("--cache-gb", type=float, default=100.0, help="per-GPU feature-cache budget used by --kg auto")
     ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (own scratch + stream each)")
     ap.add_argument("--overlap", type=int, default=2, choices=[0, 1, 2],
                     help="0 one stream; 1 gathers overlap the next hop; 2 pipelined across the two batch slots")

@@ -104,7 +104,8 @@ __device__ __forceinline__ int32_t warp_incl_scan(int32_t v, int lane) {
 // ---- single-pass chained scan (decoupled look-back).  state[t] = flag<<32 | value,
 //      flag 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.  Called by one full warp;
 //      tiles are claimed through an atomic ticket so every predecessor is already running. ----
-constexpr int kLookbackWide = 8;  // predecessor windows (32 tiles each) fetched per L2 round trip
+// kLookbackWide = predecessor windows (32 tiles each) fetched per L2 round trip
+template <int kLookbackWide>
 __device__ __forceinline__ int32_t lookback_exclusive(u64* state, int tile, int32_t aggregate, int lane) {
   if (tile == 0) {
     if (lane == 0) st_relaxed(state, (2ull << 32) | (uint32_t)aggregate);

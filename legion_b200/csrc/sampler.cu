@@ -110,6 +110,7 @@ struct SampleArgs {
   int32_t hop;
   int32_t fanout;
   uint32_t batch_id, stream_id, k0, k1;
+  int32_t wide_lookback;
 };
 
 template <int TILE_F, int RNG>
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
       if (lane < kBlock / 32) s_warp[lane] = winc - w;
       int32_t total = __shfl_sync(0xffffffffu, winc, kBlock / 32 - 1);
       // 3. chained scan across tiles
-      int32_t excl = lookback_exclusive(a.tile_state, tile, total, lane);
+      int32_t excl = a.wide_lookback ? lookback_exclusive<8>(a.tile_state, tile, total, lane)
+                                     : lookback_exclusive<1>(a.tile_state, tile, total, lane);
       if (lane == 0) {
         s_base = excl;
         if (tile == n_tiles - 1) a.ec[2] = excl + total;  // E_h (:264)
@@ -254,6 +256,7 @@ struct RankArgs {
   int32_t hop;
   int32_t ids_cap;
   int32_t* status;
+  int32_t wide_lookback;
 };
 
 __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) {
@@ -295,7 +298,8 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
       int32_t inc = warp_incl_scan(v, lane);
       s_cnt[lane] = inc - v;
       int32_t total = __shfl_sync(0xffffffffu, inc, 31);
-      int32_t excl = lookback_exclusive(a.tile_state, tile, total, lane);
+      int32_t excl = a.wide_lookback ? lookback_exclusive<8>(a.tile_state, tile, total, lane)
+                                     : lookback_exclusive<1>(a.tile_state, tile, total, lane);
       if (lane == 0) {
         s_base = excl;
         if (tile == n_tiles - 1) a.hs->new_nodes = excl + total;  // C_h (:263)
@@ -609,6 +613,8 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   a.stream_id = stream_id;
   a.k0 = (uint32_t)rng_seed;
   a.k1 = (uint32_t)(rng_seed >> 32);
+  static const int wide = [] { const char* e = getenv("LG_LOOKBACK_WIDE"); return e ? atoi(e) : 1; }();
+  a.wide_lookback = wide;
   if (rng_kind == LG_RNG_MINSTD)
     launch_sample<LG_RNG_MINSTD>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
   else
@@ -627,6 +633,7 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   r.hop = hop;
   r.ids_cap = b->num_ids;
   r.status = s->status;
+  r.wide_lookback = wide;
   rank_relabel_kernel<<<s->rank_tiles[h], kBlock, 0, st>>>(r);
   LG_LAUNCH_OK();
   return 0;
