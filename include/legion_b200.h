@@ -203,6 +203,14 @@ int lg_run_batch_host(lg_sampler* s, lg_stream_t stream, const lg_topology* topo
                       const lg_batch* batch, int32_t* host_node_counter,
                       int32_t* host_edge_counter);
 
+/* same without the final synchronisation: the host buffers (pinned) are valid once `stream` has drained past
+ * this call — several host-fed batches can be in flight, like the trainer's two pipeline slots */
+int lg_run_batch_host_async(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
+                            const lg_feature_cache* cache, const lg_batch_params* p,
+                            const int32_t* host_seed_ids, const int32_t* host_seed_labels,
+                            const lg_batch* batch, int32_t* host_node_counter,
+                            int32_t* host_edge_counter);
+
 /* ---- standalone gather (the roofline kernel) : dst[r,:] = row of ids[r] for r in [0,n) ---- */
 int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache, const int32_t* ids,
                    int64_t n, float* dst, int32_t local_part, int32_t variant,

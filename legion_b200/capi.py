@@ -67,6 +67,8 @@ _PROTOS = {
                                C.POINTER(Batch), vp]),
     "lg_run_batch_host": (C.c_int, [vp, vp, C.POINTER(Topology), C.POINTER(FeatureCache), C.POINTER(BatchParams),
                                     vp, vp, C.POINTER(Batch), vp, vp]),
+    "lg_run_batch_host_async": (C.c_int, [vp, vp, C.POINTER(Topology), C.POINTER(FeatureCache), C.POINTER(BatchParams),
+                                          vp, vp, C.POINTER(Batch), vp, vp]),
     "lg_gather_rows": (C.c_int, [vp, C.POINTER(FeatureCache), vp, C.c_int64, vp, C.c_int32, C.c_int32, vp]),
     "lg_hotness_accumulate": (C.c_int, [vp, vp, vp, C.c_int64]),
     "lg_hotness_rank": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.POINTER(C.c_int64)]),

@@ -704,11 +704,11 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
   return lg_io_complete(s, stream, p->mode, b, nullptr, nullptr);
 }
 
-extern "C" int lg_run_batch_host(lg_sampler* s, lg_stream_t stream_, const lg_topology* topo,
-                                 const lg_feature_cache* cache, const lg_batch_params* p,
-                                 const int32_t* host_seed_ids, const int32_t* host_seed_labels, const lg_batch* b,
-                                 int32_t* host_node_counter, int32_t* host_edge_counter) {
-  LG_REQUIRE(s && p && host_seed_ids && host_seed_labels && host_node_counter && host_edge_counter,
+static int run_batch_host_impl(lg_sampler* s, lg_stream_t stream_, const lg_topology* topo,
+                               const lg_feature_cache* cache, const lg_batch_params* p, const int32_t* host_seed_ids,
+                               const int32_t* host_seed_labels, const lg_batch* b, int32_t* host_node_counter,
+                               int32_t* host_edge_counter, bool sync) {
+  LG_REQUIRE(s && p && b && host_seed_ids && host_seed_labels && host_node_counter && host_edge_counter,
              "lg_run_batch_host: null argument");
   LG_REQUIRE(p->batch_size <= s->max_batch, "lg_run_batch_host: batch %d > max_batch %d", p->batch_size, s->max_batch);
   cudaStream_t st = (cudaStream_t)stream_;
@@ -725,10 +725,30 @@ extern "C" int lg_run_batch_host(lg_sampler* s, lg_stream_t stream_, const lg_to
   q.counter = 0;
   int rc = lg_run_batch(s, stream_, topo, cache, &q, b, nullptr);
   if (rc) return rc;
+  // what get_next reads back (training_backend/ipc_cuda_kernel.cu:194-195); in pipelined mode the counters
+  // are final once the sampler (caller's stream) is done, the features once lg_batch_wait has passed
+  rc = lg_batch_wait(s, stream_, b);
+  if (rc) return rc;
   LG_CUDA(cudaMemcpyAsync(host_node_counter, b->node_counter, LG_COUNTER_SLOTS * sizeof(int32_t),
                           cudaMemcpyDeviceToHost, st));
   LG_CUDA(cudaMemcpyAsync(host_edge_counter, b->edge_counter, LG_COUNTER_SLOTS * sizeof(int32_t),
                           cudaMemcpyDeviceToHost, st));
-  LG_CUDA(cudaStreamSynchronize(st));
+  if (sync) LG_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+extern "C" int lg_run_batch_host(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
+                                 const lg_feature_cache* cache, const lg_batch_params* p,
+                                 const int32_t* host_seed_ids, const int32_t* host_seed_labels, const lg_batch* b,
+                                 int32_t* host_node_counter, int32_t* host_edge_counter) {
+  return run_batch_host_impl(s, stream, topo, cache, p, host_seed_ids, host_seed_labels, b, host_node_counter,
+                             host_edge_counter, true);
+}
+
+extern "C" int lg_run_batch_host_async(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
+                                       const lg_feature_cache* cache, const lg_batch_params* p,
+                                       const int32_t* host_seed_ids, const int32_t* host_seed_labels,
+                                       const lg_batch* b, int32_t* host_node_counter, int32_t* host_edge_counter) {
+  return run_batch_host_impl(s, stream, topo, cache, p, host_seed_ids, host_seed_labels, b, host_node_counter,
+                             host_edge_counter, false);
 }

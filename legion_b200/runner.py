@@ -336,6 +336,14 @@ class DataPath:
                                        C.c_void_p(host_ids.ctypes.data), C.c_void_p(host_labels.ctypes.data),
                                        C.byref(buf.c), C.c_void_p(host_nc.ctypes.data), C.c_void_p(host_ec.ctypes.data)))
 
+    def run_once_host_async(self, p, host_ids, host_labels, buf, host_nc, host_ec, gather=True):
+        """as run_once_host without the final synchronisation (host buffers must be pinned)"""
+        check(self.L.lg_run_batch_host_async(self.sampler, self._stream(), C.byref(self.topo),
+                                             C.byref(self.cache) if gather else None, C.byref(p),
+                                             C.c_void_p(host_ids.ctypes.data), C.c_void_p(host_labels.ctypes.data),
+                                             C.byref(buf.c), C.c_void_p(host_nc.ctypes.data),
+                                             C.c_void_p(host_ec.ctypes.data)))
+
     def run_presc(self, p, buf, edge_hot, node_hot, max_ids):
         """GPURunner::RunPreSc (engine/server.cu:285-300): ops 0,3,6,..,last with is_presc=true"""
         st = self._stream()
