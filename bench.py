@@ -489,6 +489,7 @@ def cpu_arm(shape, indptr, indices, feat, train, steps, warmup):
     from oracle import oracle as O
     B, fanout, D = shape["batch"], shape["fanout"], shape["D"]
     base = O.DGLBaseline(indptr, indices, fanout, B)
+    base.use_all_cores()  # torchrun sets OMP_NUM_THREADS=1; the CPU arm gets every host core
     out = np.empty((O.num_ids(B, fanout), D), np.float32)
     n_batches = (len(train) - 1) // B
     times, rows = [], 0

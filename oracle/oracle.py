@@ -70,6 +70,7 @@ def lib():
                                  i32p, i64p, i64p, i64p, i32p]
     L.lgo_index_select.argtypes = [f32p, C.c_int32, i32p, C.c_int64, f32p]
     L.lgo_num_threads.restype = C.c_int32
+    L.lgo_set_num_threads.argtypes = [C.c_int32]
     _lib = L
     return L
 
@@ -258,3 +259,7 @@ class DGLBaseline:
 
     def threads(self):
         return int(self.L.lgo_num_threads())
+
+    def use_all_cores(self):
+        self.L.lgo_set_num_threads(os.cpu_count() or 1)
+        return self.threads()
