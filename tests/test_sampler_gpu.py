@@ -307,3 +307,32 @@ def test_two_runners_in_flight_on_one_gpu(oracle):
             want = orc.run_batch(ids, labels, B, 2 * rnd + k, seed=3, batch_id=2 * rnd + k)
             assert_batch_equal(buf.to_host(2), want, 2, feat)
     d2.close()
+
+
+def test_async_host_fed_batches(oracle):
+    """lg_run_batch_host_async: several host-fed batches in flight, counters land in pinned memory"""
+    indptr, indices = small_graph()
+    N = len(indptr) - 1
+    feat = _feat(N, 100)
+    ids, labels = make_sets(N)
+    fanout, B = [5, 3], 64
+    rig = Rig(indptr, indices, feat, fanout, B)
+    rig.dp.set_overlap(2)
+    rig.dp.set_gather_fusion(2)
+    d_ids, d_lab = rig.sets(ids, labels)
+    bufs = [rig.dp.alloc_batch(), rig.dp.alloc_batch()]
+    h_ids = torch.from_numpy(ids.copy()).pin_memory()
+    h_lab = torch.from_numpy(labels.copy()).pin_memory()
+    cnt = torch.zeros((4, 32), dtype=torch.int32).pin_memory()
+    cn = cnt.numpy()
+    orc = oracle.Oracle(indptr, indices, fanout, B)
+    for it in range(4):
+        p = rig.dp.params(d_ids, d_lab, B, it, seed=6, batch_id=it)
+        rig.dp.run_once_host_async(p, h_ids.numpy()[it * B:(it + 1) * B], h_lab.numpy()[it * B:(it + 1) * B], bufs[it % 2],
+                                   cn[it, :16], cn[it, 16:])
+        if it % 2 == 1:  # consume the two slots before they are reused
+            torch.cuda.synchronize()
+            for k in (it - 1, it):
+                want = orc.run_batch(ids, labels, B, k, seed=6, batch_id=k)
+                assert np.array_equal(cn[k, :16], want["nc"]) and np.array_equal(cn[k, 16:], want["ec"])
+                assert_batch_equal(bufs[k % 2].to_host(2), want, 2, feat)
