@@ -104,8 +104,6 @@ __device__ __forceinline__ int32_t warp_incl_scan(int32_t v, int lane) {
 // ---- single-pass chained scan (decoupled look-back).  state[t] = flag<<32 | value,
 //      flag 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.  Called by one full warp;
 //      tiles are claimed through an atomic ticket so every predecessor is already running. ----
-// kLookbackWide = predecessor windows (32 tiles each) fetched per L2 round trip
-template <int kLookbackWide>
 __device__ __forceinline__ int32_t lookback_exclusive(u64* state, int tile, int32_t aggregate, int lane) {
   if (tile == 0) {
     if (lane == 0) st_relaxed(state, (2ull << 32) | (uint32_t)aggregate);
@@ -114,34 +112,21 @@ __device__ __forceinline__ int32_t lookback_exclusive(u64* state, int tile, int3
   if (lane == 0) st_relaxed(state + tile, (1ull << 32) | (uint32_t)aggregate);
   int32_t excl = 0;
   int look = tile - 1;
-  bool done = false;
-  while (!done) {
-    // all kLookbackWide windows are requested before any is consumed: one round trip covers 256 tiles
-    // (a wave of ~900 resident tiles would otherwise walk ~28 dependent L2 reads)
-    u64 s[kLookbackWide];
-#pragma unroll
-    for (int j = 0; j < kLookbackWide; j++) {
-      const int idx = look - lane - 32 * j;
-      s[j] = (idx >= 0) ? ld_relaxed(state + idx) : (2ull << 32);
+  while (true) {
+    int idx = look - lane;
+    u64 s = (idx >= 0) ? ld_relaxed(state + idx) : (2ull << 32);
+    while (__any_sync(0xffffffffu, (s >> 32) == 0ull)) {
+      if ((s >> 32) == 0ull) s = ld_relaxed(state + idx);
     }
-#pragma unroll
-    for (int j = 0; j < kLookbackWide; j++) {
-      if (done) break;
-      const int idx = look - lane - 32 * j;
-      while (__any_sync(0xffffffffu, (s[j] >> 32) == 0ull)) {
-        if ((s[j] >> 32) == 0ull) s[j] = ld_relaxed(state + idx);
-      }
-      const unsigned pre = __ballot_sync(0xffffffffu, (s[j] >> 32) == 2ull);
-      const int32_t v = (int32_t)(uint32_t)s[j];
-      if (pre) {
-        const int first = __ffs(pre) - 1;
-        excl += warp_sum(lane <= first ? v : 0);
-        done = true;
-      } else {
-        excl += warp_sum(v);
-      }
+    unsigned done = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
+    int32_t v = (int32_t)(uint32_t)s;
+    if (done) {
+      int first = __ffs(done) - 1;
+      excl += warp_sum(lane <= first ? v : 0);
+      break;
     }
-    look -= 32 * kLookbackWide;
+    excl += warp_sum(v);
+    look -= 32;
   }
   if (lane == 0) st_relaxed(state + tile, (2ull << 32) | (uint32_t)(excl + aggregate));
   return excl;

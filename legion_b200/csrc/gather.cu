@@ -31,7 +31,6 @@ struct GatherArgs {
   int32_t local_part;
   u64* tier;           // [3] local / peer / miss rows, may be null
   int32_t* status;
-  int32_t hot_rows;    // shard rows [0, hot_rows) are the hottest ranks: their loads ask L2 to keep them
 };
 
 __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int64_t* cnt) {
@@ -54,9 +53,8 @@ __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int
 }
 
 // location decode: returns the source row pointer or nullptr (row is skipped), tier in *t
-__device__ __forceinline__ const float* locate(const GatherArgs& a, int32_t id, int* t, bool* hot) {
+__device__ __forceinline__ const float* locate(const GatherArgs& a, int32_t id, int* t) {
   *t = -1;
-  *hot = false;
   if (id < 0) return nullptr;  // -1 padding of a tail batch (cache_impl.cuh:263-264)
   int32_t gidx = LG_CACHEMISS_FLAG;
   if (a.cache.directory && id < a.cache.num_nodes) gidx = a.cache.directory[id];
@@ -71,7 +69,6 @@ __device__ __forceinline__ const float* locate(const GatherArgs& a, int32_t id, 
   int32_t didx = gidx / a.cache.shard_rows;  // cache_impl.cuh:259-260
   int32_t fidx = gidx - didx * a.cache.shard_rows;
   *t = (didx == a.local_part) ? 0 : 1;
-  *hot = fidx < a.hot_rows;
   return a.cache.shard[didx] + (int64_t)fidx * a.cache.dim;
 }
 
@@ -84,29 +81,6 @@ __device__ __forceinline__ float4 ld_nc_v4(const float* p) {
 }
 __device__ __forceinline__ void st_v4(float* p, const float4& v) {
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-__device__ __forceinline__ u64 policy_evict_last() {
-  u64 p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ u64 policy_evict_first() {
-  u64 p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ld_nc_v4_hint(const float* p, u64 pol) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p), "l"(pol));
-  return r;
-}
-__device__ __forceinline__ void st_v4_hint(float* p, const float4& v, u64 pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
-               "l"(pol)
-               : "memory");
 }
 
 __device__ __forceinline__ void tier_flush(const GatherArgs& a, int32_t t0, int32_t t1, int32_t t2, int lane) {
@@ -122,10 +96,9 @@ __device__ __forceinline__ void tier_flush(const GatherArgs& a, int32_t t0, int3
 }
 
 // ---------------- LDG mover: warp per R consecutive rows ----------------
-// HINT: 0 = no L2 policy; 1 = output stores evict-first (written once, read later by the trainer);
-//       2 = 1 + hot cache rows evict-last / cold rows evict-first (keeps the head of the
-//           hotness-ranked shard resident in the 126 MB L2 across batches)
-template <int R, bool VEC4, int HINT>
+// (an L2 eviction-policy variant — evict-first output stores, evict-last loads for the hottest ranks —
+//  was measured and lost 4-12 %: profiles/r01_gather_sweep_v1.txt)
+template <int R, bool VEC4>
 __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
   int64_t off, cnt;
   row_range(a, &off, &cnt);
@@ -134,18 +107,13 @@ __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int dim = a.cache.dim;
   int32_t t0 = 0, t1 = 0, t2 = 0;
-  u64 pol_first = 0, pol_last = 0;
-  if (HINT >= 1) pol_first = policy_evict_first();
-  if (HINT >= 2) pol_last = policy_evict_last();
   for (int64_t r0 = warp_global * R; r0 < cnt; r0 += n_warps * R) {
-    u64 src = 0;  // bit 0 = hot row
+    const float* src = nullptr;
     if (lane < R && r0 + lane < cnt) {
       int64_t row = off + r0 + lane;
       if (row < a.dst_rows) {
         int t;
-        bool hot;
-        src = (u64)locate(a, a.ids[row], &t, &hot);
-        if (src && hot) src |= 1ull;
+        src = locate(a, a.ids[row], &t);
         t0 += (t == 0);
         t1 += (t == 1);
         t2 += (t == 2);
@@ -158,32 +126,20 @@ __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
       for (int c0 = 0; c0 < d4; c0 += 32) {
         const int c = c0 + lane;
         float4 v[R];
-        u64 sk[R];
+        const float* sk[R];
 #pragma unroll
         for (int k = 0; k < R; k++) {
-          sk[k] = __shfl_sync(0xffffffffu, src, k);
-          if (sk[k] && c < d4) {
-            const float* p = (const float*)(sk[k] & ~1ull) + 4 * c;
-            if (HINT >= 2)
-              v[k] = ld_nc_v4_hint(p, (sk[k] & 1ull) ? pol_last : pol_first);
-            else
-              v[k] = ld_nc_v4(p);
-          }
+          sk[k] = (const float*)__shfl_sync(0xffffffffu, (u64)src, k);
+          if (sk[k] && c < d4) v[k] = ld_nc_v4(sk[k] + 4 * c);
         }
 #pragma unroll
         for (int k = 0; k < R; k++)
-          if (sk[k] && c < d4) {
-            float* d = a.dst + (off + r0 + k) * dim + 4 * c;
-            if (HINT >= 1)
-              st_v4_hint(d, v[k], pol_first);
-            else
-              st_v4(d, v[k]);
-          }
+          if (sk[k] && c < d4) st_v4(a.dst + (off + r0 + k) * dim + 4 * c, v[k]);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < R; k++) {
-        const float* s = (const float*)(__shfl_sync(0xffffffffu, src, k) & ~1ull);
+        const float* s = (const float*)__shfl_sync(0xffffffffu, (u64)src, k);
         if (!s) continue;
         float* d = a.dst + (off + r0 + k) * dim;
         for (int c = lane; c < dim; c += 32) d[c] = __ldg(s + c);
@@ -338,18 +294,16 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   tier_flush(a, t0, t1, t2, lane);
 }
 
-// tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {2,4,8}, LG_LDG_HINT {0,1,2},
-// LG_TMA_STAGES {3,4,6,8}, LG_HOT_MB size of the L2-resident head of each shard
+// tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {4,8}, LG_TMA_STAGES {3,4,6},
+// LG_LDG_CTAS resident CTAs per SM assumed when sizing the LDG grid
 struct Tune {
-  int ldg_r, ldg_hint, tma_stages, hot_mb, ldg_ctas;
+  int ldg_r, tma_stages, ldg_ctas;
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 0, 3, 64, 8};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM)
+    Tune x{8, 3, 8};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
-    if (const char* e = getenv("LG_LDG_HINT")) x.ldg_hint = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
-    if (const char* e = getenv("LG_HOT_MB")) x.hot_mb = atoi(e);
     if (const char* e = getenv("LG_LDG_CTAS")) x.ldg_ctas = atoi(e);
     return x;
   }();
@@ -371,7 +325,7 @@ int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
   return 0;
 }
 
-template <int R, int HINT>
+template <int R>
 int launch_ldg(cudaStream_t st, const GatherArgs& a, int64_t max_rows, bool vec_ok) {
   int64_t warps = (max_rows + R - 1) / R;
   int64_t grid = (warps + 7) / 8;
@@ -379,9 +333,9 @@ int launch_ldg(cudaStream_t st, const GatherArgs& a, int64_t max_rows, bool vec_
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   if (vec_ok)
-    gather_ldg_kernel<R, true, HINT><<<(int)grid, 256, 0, st>>>(a);
+    gather_ldg_kernel<R, true><<<(int)grid, 256, 0, st>>>(a);
   else
-    gather_ldg_kernel<R, false, 0><<<(int)grid, 256, 0, st>>>(a);
+    gather_ldg_kernel<R, false><<<(int)grid, 256, 0, st>>>(a);
   LG_LAUNCH_OK();
   return 0;
 }
@@ -390,28 +344,18 @@ int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) 
   const int dim = a.cache.dim;
   const bool vec_ok = (dim % 4 == 0) && (((uintptr_t)a.dst & 15) == 0) && (((uintptr_t)a.cache.backing & 15) == 0);
   const Tune& t = tune();
-  a.hot_rows = (int32_t)(((int64_t)t.hot_mb << 20) / ((int64_t)dim * 4));
   if (variant == LG_GATHER_AUTO) variant = LG_GATHER_TMA;  // falls through to LDG when rows are not 16-byte multiples
   if (variant == LG_GATHER_TMA && vec_ok && (size_t)dim * 4 * kTmaRows * 3 <= 200 * 1024) {
     int stages = t.tma_stages;
     while (stages > 3 && (size_t)dim * 4 * kTmaRows * stages > 200 * 1024) stages--;
     switch (stages) {
-      case 3: return launch_tma<3>(st, a, max_rows);
+      case 4: return launch_tma<4>(st, a, max_rows);
       case 6: return launch_tma<6>(st, a, max_rows);
-      case 8: return launch_tma<8>(st, a, max_rows);
-      default: return launch_tma<4>(st, a, max_rows);
+      default: return launch_tma<3>(st, a, max_rows);
     }
   }
-  const int key = t.ldg_r * 10 + t.ldg_hint;
-  switch (key) {
-    case 20: return launch_ldg<2, 0>(st, a, max_rows, vec_ok);
-    case 21: return launch_ldg<2, 1>(st, a, max_rows, vec_ok);
-    case 22: return launch_ldg<2, 2>(st, a, max_rows, vec_ok);
-    case 40: return launch_ldg<4, 0>(st, a, max_rows, vec_ok);
-    case 41: return launch_ldg<4, 1>(st, a, max_rows, vec_ok);
-    case 42: return launch_ldg<4, 2>(st, a, max_rows, vec_ok);
-    default: return launch_ldg<8, 0>(st, a, max_rows, vec_ok);
-  }
+  if (t.ldg_r == 4) return launch_ldg<4>(st, a, max_rows, vec_ok);
+  return launch_ldg<8>(st, a, max_rows, vec_ok);
 }
 
 int check_cache(const lg_feature_cache* c) {
@@ -455,7 +399,6 @@ extern "C" int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, 
   a.local_part = local_part;
   a.tier = (u64*)tier_rows;
   a.status = s->status;
-  a.hot_rows = 0;
   LG_REQUIRE(a.hop <= s->n_hops, "lg_feature_cache_lookup: op_id %d beyond %d hops", op_id, s->n_hops);
   int64_t max_rows = 0;
   for (int h = first_hop; h <= a.hop; h++) max_rows += s->slots_per_hop[h];
@@ -484,6 +427,5 @@ extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache,
   a.local_part = local_part;
   a.tier = (u64*)tier_rows;
   a.status = dummy_status;
-  a.hot_rows = 0;
   return launch_gather((cudaStream_t)stream, a, variant, n);
 }

@@ -32,11 +32,16 @@ constexpr int kRankTile = kBlock * kRankItems;     // 1024 edges per tile
 static_assert(kRankItems * (kBlock / 32) == 32, "rank tile partial counts must fill one warp");
 constexpr int kSlotUnroll = 4;                     // neighbour reads in flight per thread in sample_hop_kernel
 
+// Insert-min of (key -> val).  The pre-check reads the slot through L1 (ld.ca): popular vertices are sampled
+// thousands of times per batch, and sending every one of those reads to the single L2 slice that owns the
+// slot serialises the whole kernel.  A stale line is harmless: keys never change once written, values only
+// decrease, so a stale value can only make us issue an atomic that turns out to be a no-op — never skip
+// one that was needed (stale >= actual, and we skip only when stale <= val).
 __device__ __forceinline__ void table_insert_min(u64* table, uint32_t mask, int32_t key, uint32_t val) {
   uint32_t slot = hash32((uint32_t)key) & mask;
   const u64 packed = ((u64)(uint32_t)key << 32) | val;
   while (true) {
-    u64 cur = ld_relaxed(table + slot);
+    u64 cur = __ldca(table + slot);
     if (cur == kEmpty) {
       cur = atomicCAS(table + slot, kEmpty, packed);
       if (cur == kEmpty) return;
@@ -48,11 +53,13 @@ __device__ __forceinline__ void table_insert_min(u64* table, uint32_t mask, int3
     slot = (slot + 1) & mask;
   }
 }
-// key must be present
+// key must be present.  `cached`: probe through L1 — valid when the caller only needs the key/slot or a value
+// that cannot have changed since the kernel started (keys are immutable within a batch).
+template <bool CACHED>
 __device__ __forceinline__ uint32_t table_find(const u64* table, uint32_t mask, int32_t key, u64* word) {
   uint32_t slot = hash32((uint32_t)key) & mask;
   while (true) {
-    u64 cur = ld_relaxed(table + slot);
+    u64 cur = CACHED ? __ldca(table + slot) : ld_relaxed(table + slot);
     if ((uint32_t)(cur >> 32) == (uint32_t)key || cur == kEmpty) {
       *word = cur;
       return slot;
@@ -110,7 +117,6 @@ struct SampleArgs {
   int32_t hop;
   int32_t fanout;
   uint32_t batch_id, stream_id, k0, k1;
-  int32_t wide_lookback;
 };
 
 template <int TILE_F, int RNG>
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
       if (v >= 0) {
         if (first_hop) {
           u64 w;
-          table_find(a.table, a.mask, v, &w);
+          table_find<true>(a.table, a.mask, v, &w);
           fl = (int32_t)(uint32_t)w;
         } else {
           fl = a.agg_src[prev_edge_off + i];
@@ -195,8 +201,7 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
       if (lane < kBlock / 32) s_warp[lane] = winc - w;
       int32_t total = __shfl_sync(0xffffffffu, winc, kBlock / 32 - 1);
       // 3. chained scan across tiles
-      int32_t excl = a.wide_lookback ? lookback_exclusive<8>(a.tile_state, tile, total, lane)
-                                     : lookback_exclusive<1>(a.tile_state, tile, total, lane);
+      int32_t excl = lookback_exclusive(a.tile_state, tile, total, lane);
       if (lane == 0) {
         s_base = excl;
         if (tile == n_tiles - 1) a.ec[2] = excl + total;  // E_h (:264)
@@ -256,7 +261,6 @@ struct RankArgs {
   int32_t hop;
   int32_t ids_cap;
   int32_t* status;
-  int32_t wide_lookback;
 };
 
 __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) {
@@ -286,7 +290,10 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
       if (p < E) {
         w[k] = a.gid[p];
         u64 word;
-        slot[k] = table_find(a.table, a.mask, w[k], &word);
+        // L1-cached probe: a line fetched before the owner publishes still holds kNewBit|p_first, one fetched
+        // after holds the final id — neither can equal kNewBit|p for a non-owner, and the owner's own word
+        // is only ever rewritten by the owner itself
+        slot[k] = table_find<true>(a.table, a.mask, w[k], &word);
         first[k] = ((uint32_t)word == (kNewBit | (uint32_t)p));
       }
       bal[k] = __ballot_sync(0xffffffffu, first[k]);
@@ -298,8 +305,7 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
       int32_t inc = warp_incl_scan(v, lane);
       s_cnt[lane] = inc - v;
       int32_t total = __shfl_sync(0xffffffffu, inc, 31);
-      int32_t excl = a.wide_lookback ? lookback_exclusive<8>(a.tile_state, tile, total, lane)
-                                     : lookback_exclusive<1>(a.tile_state, tile, total, lane);
+      int32_t excl = lookback_exclusive(a.tile_state, tile, total, lane);
       if (lane == 0) {
         s_base = excl;
         if (tile == n_tiles - 1) a.hs->new_nodes = excl + total;  // C_h (:263)
@@ -325,7 +331,10 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
       int32_t p = p0 + k * kBlock + tid;
       if (p < E && !first[k]) {
         u64 word = ld_relaxed(a.table + slot[k]);
-        while ((uint32_t)word & kNewBit) word = ld_relaxed(a.table + slot[k]);
+        while ((uint32_t)word & kNewBit) {  // back off: thousands of repeats of a hub vertex poll the same word
+          __nanosleep(64);
+          word = ld_relaxed(a.table + slot[k]);
+        }
         a.agg_src[edge_base + p] = (int32_t)(uint32_t)word;  // construct_graph :291,293
       }
     }
@@ -613,8 +622,7 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   a.stream_id = stream_id;
   a.k0 = (uint32_t)rng_seed;
   a.k1 = (uint32_t)(rng_seed >> 32);
-  static const int wide = [] { const char* e = getenv("LG_LOOKBACK_WIDE"); return e ? atoi(e) : 1; }();
-  a.wide_lookback = wide;
+
   if (rng_kind == LG_RNG_MINSTD)
     launch_sample<LG_RNG_MINSTD>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
   else
@@ -633,7 +641,6 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   r.hop = hop;
   r.ids_cap = b->num_ids;
   r.status = s->status;
-  r.wide_lookback = wide;
   rank_relabel_kernel<<<s->rank_tiles[h], kBlock, 0, st>>>(r);
   LG_LAUNCH_OK();
   return 0;
