@@ -53,6 +53,33 @@ __device__ __forceinline__ void table_insert_min(u64* table, uint32_t mask, int3
     slot = (slot + 1) & mask;
   }
 }
+// Batched form: the caller has already loaded `cur` = table[slot] for several keys at once (memory-level
+// parallelism across a thread's slots) and, for empty slots, already issued the CAS (`cur` = its return value,
+// `claimed` = the CAS found the slot empty).  Finishes the insert; falls back to linear probing on a collision.
+__device__ __forceinline__ void table_insert_finish(u64* table, uint32_t mask, int32_t key, uint32_t val, uint32_t slot,
+                                                    u64 cur, bool claimed) {
+  if (claimed) return;
+  if ((uint32_t)(cur >> 32) == (uint32_t)key) {
+    if ((uint32_t)cur > val) atomicMin(table + slot, ((u64)(uint32_t)key << 32) | val);
+    return;
+  }
+  // another key owns this slot: continue with the generic probe sequence from the next slot
+  const u64 packed = ((u64)(uint32_t)key << 32) | val;
+  slot = (slot + 1) & mask;
+  while (true) {
+    cur = __ldca(table + slot);
+    if (cur == kEmpty) {
+      cur = atomicCAS(table + slot, kEmpty, packed);
+      if (cur == kEmpty) return;
+    }
+    if ((uint32_t)(cur >> 32) == (uint32_t)key) {
+      if ((uint32_t)cur > val) atomicMin(table + slot, packed);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
 // key must be present.  `cached`: probe through L1 — valid when the caller only needs the key/slot or a value
 // that cannot have changed since the kernel started (keys are immutable within a batch).
 template <bool CACHED>
@@ -234,14 +261,30 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
         }
       }
     }
+    // dedup-table insert-min, batched: all first probes in flight together, then all claims, then the rest
+    uint32_t sl[kSlotUnroll];
+    u64 cur[kSlotUnroll];
 #pragma unroll
     for (int u = 0; u < kSlotUnroll; u++) {
       if (p[u] >= 0) {
         a.gid_out[p[u]] = w[u];
         a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
-        table_insert_min(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u]);
+        sl[u] = hash32((uint32_t)w[u]) & a.mask;
+        cur[u] = __ldca(a.table + sl[u]);
       }
     }
+    bool claimed[kSlotUnroll];
+#pragma unroll
+    for (int u = 0; u < kSlotUnroll; u++) {
+      claimed[u] = false;
+      if (p[u] >= 0 && cur[u] == kEmpty) {
+        cur[u] = atomicCAS(a.table + sl[u], kEmpty, ((u64)(uint32_t)w[u] << 32) | (kNewBit | (uint32_t)p[u]));
+        claimed[u] = (cur[u] == kEmpty);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSlotUnroll; u++)
+      if (p[u] >= 0) table_insert_finish(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u], sl[u], cur[u], claimed[u]);
   }
 }
 
@@ -281,20 +324,30 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
     uint32_t slot[kRankItems];
     bool first[kRankItems];
     unsigned bal[kRankItems];
+    u64 word[kRankItems];
+#pragma unroll
+    for (int k = 0; k < kRankItems; k++) {  // all first probes of the thread's edges in flight together
+      const int32_t p = p0 + k * kBlock + tid;
+      w[k] = (p < E) ? a.gid[p] : -1;
+    }
 #pragma unroll
     for (int k = 0; k < kRankItems; k++) {
-      int32_t p = p0 + k * kBlock + tid;
+      slot[k] = hash32((uint32_t)w[k]) & a.mask;
+      // L1-cached probe: a line fetched before the owner publishes still holds kNewBit|p_first, one fetched
+      // after holds the final id — neither can equal kNewBit|p for a non-owner, and the owner's own word is
+      // only ever rewritten by the owner itself
+      word[k] = (w[k] >= 0) ? __ldca(a.table + slot[k]) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < kRankItems; k++) {
+      const int32_t p = p0 + k * kBlock + tid;
       first[k] = false;
-      w[k] = -1;
-      slot[k] = 0;
-      if (p < E) {
-        w[k] = a.gid[p];
-        u64 word;
-        // L1-cached probe: a line fetched before the owner publishes still holds kNewBit|p_first, one fetched
-        // after holds the final id — neither can equal kNewBit|p for a non-owner, and the owner's own word
-        // is only ever rewritten by the owner itself
-        slot[k] = table_find<true>(a.table, a.mask, w[k], &word);
-        first[k] = ((uint32_t)word == (kNewBit | (uint32_t)p));
+      if (w[k] >= 0) {
+        while ((uint32_t)(word[k] >> 32) != (uint32_t)w[k] && word[k] != kEmpty) {  // collision: next slot
+          slot[k] = (slot[k] + 1) & a.mask;
+          word[k] = __ldca(a.table + slot[k]);
+        }
+        first[k] = ((uint32_t)word[k] == (kNewBit | (uint32_t)p));
       }
       bal[k] = __ballot_sync(0xffffffffu, first[k]);
       if (lane == 0) s_cnt[k * (kBlock / 32) + warp] = __popc(bal[k]);
