@@ -146,7 +146,7 @@ struct SampleArgs {
   uint32_t batch_id, stream_id, k0, k1;
 };
 
-template <int TILE_F, int RNG>
+template <int TILE_F, int RNG, int INS>
 __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) {
   __shared__ long long s_start[TILE_F];
   __shared__ int32_t s_deg[TILE_F];
@@ -261,30 +261,53 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
         }
       }
     }
-    // dedup-table insert-min, batched: all first probes in flight together, then all claims, then the rest
-    uint32_t sl[kSlotUnroll];
-    u64 cur[kSlotUnroll];
+    // dedup-table insert-min.  INS 0: one slot after the other; 1: all first probes of the group in flight
+    // together, claims one by one; 2: probes and claims both batched
+    if (INS == 0) {
 #pragma unroll
-    for (int u = 0; u < kSlotUnroll; u++) {
-      if (p[u] >= 0) {
-        a.gid_out[p[u]] = w[u];
-        a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
-        sl[u] = hash32((uint32_t)w[u]) & a.mask;
-        cur[u] = __ldca(a.table + sl[u]);
+      for (int u = 0; u < kSlotUnroll; u++) {
+        if (p[u] >= 0) {
+          a.gid_out[p[u]] = w[u];
+          a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
+          table_insert_min(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u]);
+        }
+      }
+    } else {
+      uint32_t sl[kSlotUnroll];
+      u64 cur[kSlotUnroll];
+#pragma unroll
+      for (int u = 0; u < kSlotUnroll; u++) {
+        if (p[u] >= 0) {
+          a.gid_out[p[u]] = w[u];
+          a.agg_dst[edge_base + p[u]] = fl[u];
+          sl[u] = hash32((uint32_t)w[u]) & a.mask;
+          cur[u] = __ldca(a.table + sl[u]);
+        }
+      }
+      bool claimed[kSlotUnroll];
+      if (INS == 2) {
+#pragma unroll
+        for (int u = 0; u < kSlotUnroll; u++) {
+          claimed[u] = false;
+          if (p[u] >= 0 && cur[u] == kEmpty) {
+            cur[u] = atomicCAS(a.table + sl[u], kEmpty, ((u64)(uint32_t)w[u] << 32) | (kNewBit | (uint32_t)p[u]));
+            claimed[u] = (cur[u] == kEmpty);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSlotUnroll; u++) {
+        if (p[u] < 0) continue;
+        if (INS == 1) {
+          claimed[u] = false;
+          if (cur[u] == kEmpty) {
+            cur[u] = atomicCAS(a.table + sl[u], kEmpty, ((u64)(uint32_t)w[u] << 32) | (kNewBit | (uint32_t)p[u]));
+            claimed[u] = (cur[u] == kEmpty);
+          }
+        }
+        table_insert_finish(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u], sl[u], cur[u], claimed[u]);
       }
     }
-    bool claimed[kSlotUnroll];
-#pragma unroll
-    for (int u = 0; u < kSlotUnroll; u++) {
-      claimed[u] = false;
-      if (p[u] >= 0 && cur[u] == kEmpty) {
-        cur[u] = atomicCAS(a.table + sl[u], kEmpty, ((u64)(uint32_t)w[u] << 32) | (kNewBit | (uint32_t)p[u]));
-        claimed[u] = (cur[u] == kEmpty);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kSlotUnroll; u++)
-      if (p[u] >= 0) table_insert_finish(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u], sl[u], cur[u], claimed[u]);
   }
 }
 
@@ -634,14 +657,21 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   return 0;
 }
 
+template <int RNG, int INS>
+static void launch_sample_ins(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
+  switch (tile_f) {
+    case 256: sample_hop_kernel<256, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
+    case 128: sample_hop_kernel<128, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
+    case 64: sample_hop_kernel<64, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
+    default: sample_hop_kernel<32, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
+  }
+}
 template <int RNG>
 static void launch_sample(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
-  switch (tile_f) {
-    case 256: sample_hop_kernel<256, RNG><<<grid, kBlock, 0, st>>>(a); break;
-    case 128: sample_hop_kernel<128, RNG><<<grid, kBlock, 0, st>>>(a); break;
-    case 64: sample_hop_kernel<64, RNG><<<grid, kBlock, 0, st>>>(a); break;
-    default: sample_hop_kernel<32, RNG><<<grid, kBlock, 0, st>>>(a); break;
-  }
+  static const int ins = [] { const char* e = getenv("LG_SAMPLE_INS"); return e ? atoi(e) : 0; }();
+  if (ins == 2) launch_sample_ins<RNG, 2>(tile_f, grid, st, a);
+  else if (ins == 1) launch_sample_ins<RNG, 1>(tile_f, grid, st, a);
+  else launch_sample_ins<RNG, 0>(tile_f, grid, st, a);
 }
 
 extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_topology* topo, int32_t hop,
