@@ -132,6 +132,11 @@ int lg_batch_wait(lg_sampler* s, lg_stream_t stream, const lg_batch* batch);
  * sizes it 1.2 x presampled max without a bound check, engine/server.cu:277).  Synchronises. */
 int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);
 
+/* diagnostics: per-tile phase timestamps of the sampler kernels (globaltimer ns, clock64) written to a device
+ * buffer of lg_debug_trace_words() u64 words, layout [(hop-1)*2 + kernel][tile < 2048][phase < 8][2]; NULL = off */
+int lg_debug_set_trace(lg_sampler* s, unsigned long long* device_buf);
+int64_t lg_debug_trace_words(void);
+
 /* ---- the five operator bodies (engine/operator_impl.cuh:11-63) ---- */
 
 /* BatchGenerate (engine/operator_impl.cu:27-55,92-172): seeds of batch `counter` =

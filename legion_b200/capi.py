@@ -53,6 +53,8 @@ _PROTOS = {
     "lg_sampler_set_gather_variant": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_overlap": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_gather_fusion": (C.c_int, [vp, C.c_int32]),
+    "lg_debug_set_trace": (C.c_int, [vp, vp]),
+    "lg_debug_trace_words": (C.c_int64, []),
     "lg_batch_wait": (C.c_int, [vp, vp, C.POINTER(Batch)]),
     "lg_sampler_status": (C.c_int, [vp, vp, C.POINTER(C.c_int32)]),
     "lg_batch_generate": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Batch)]),

@@ -32,6 +32,18 @@ constexpr int kRankTile = kBlock * kRankItems;     // 1024 edges per tile
 static_assert(kRankItems * (kBlock / 32) == 32, "rank tile partial counts must fill one warp");
 constexpr int kSlotUnroll = 4;                     // neighbour reads in flight per thread in sample_hop_kernel
 
+// optional per-tile phase timestamps (diagnostics only: lg_debug_set_trace; nullptr in production)
+constexpr int kTraceTiles = 2048, kTracePhases = 8;
+__device__ __forceinline__ void trace_mark(u64* trace, int kernel_slot, int tile, int phase) {
+  if (!trace || tile >= kTraceTiles) return;
+  u64 t, c;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  c = (u64)clock64();
+  u64* p = trace + ((size_t)kernel_slot * kTraceTiles + tile) * kTracePhases * 2 + phase * 2;
+  p[0] = t;
+  p[1] = c;
+}
+
 // Insert-min of (key -> val).  The pre-check reads the slot through L1 (ld.ca): popular vertices are sampled
 // thousands of times per batch, and sending every one of those reads to the single L2 slice that owns the
 // slot serialises the whole kernel.  A stale line is harmless: keys never change once written, values only
@@ -144,6 +156,7 @@ struct SampleArgs {
   int32_t hop;
   int32_t fanout;
   uint32_t batch_id, stream_id, k0, k1;
+  u64* trace;
 };
 
 template <int TILE_F, int RNG, int INS>
@@ -161,6 +174,8 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
   if (tid == 0) s_tile = atomicAdd(&a.hs->sample_ticket, 1);
   __syncthreads();
   const int tile = s_tile;
+  const int tslot = (a.hop - 1) * 2;
+  if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
 
   const bool first_hop = (a.hop == 1);
   const int32_t F = first_hop ? a.nc[1] : a.ec[1];          // :201-206
@@ -215,6 +230,7 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
     s_indices[tid] = ind;
   }
   __syncthreads();
+  if (tid == 0) trace_mark(a.trace, tslot, tile, 1);
 
   // 2. exclusive scan of the per-entry edge counts inside the tile
   {
@@ -239,6 +255,7 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
   }
   __syncthreads();
   const int32_t base = s_base;
+  if (tid == 0) trace_mark(a.trace, tslot, tile, 2);
 
   // 4. one thread per slot: pick, emit, insert-min.  kSlotUnroll independent neighbour reads are issued
   //    back to back before any of them is consumed (the read is a random 4-byte HBM/NVLink/PCIe access).
@@ -309,6 +326,11 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
       }
     }
   }
+  if (a.trace) {
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 3);  // thread 0 done
+    __syncthreads();
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 4);  // whole CTA done
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -327,6 +349,7 @@ struct RankArgs {
   int32_t hop;
   int32_t ids_cap;
   int32_t* status;
+  u64* trace;
 };
 
 __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) {
@@ -336,6 +359,8 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
   if (tid == 0) s_tile = atomicAdd(&a.hs->rank_ticket, 1);
   __syncthreads();
   const int tile = s_tile;
+  const int tslot = (a.hop - 1) * 2 + 1;
+  if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
   const int32_t E = a.ec[2];
   const int32_t node_base = a.nc[0] + a.nc[1];  // :268
   const int32_t edge_base = a.ec[0] + a.ec[1];
@@ -375,7 +400,9 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
       bal[k] = __ballot_sync(0xffffffffu, first[k]);
       if (lane == 0) s_cnt[k * (kBlock / 32) + warp] = __popc(bal[k]);
     }
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 1);  // warp 0 probes done
     __syncthreads();
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 2);  // all probes done
     if (warp == 0) {  // kRankItems * 8 == 32 partial counts, in edge order
       int32_t v = s_cnt[lane];
       int32_t inc = warp_incl_scan(v, lane);
@@ -389,6 +416,7 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
     }
     __syncthreads();
     const int32_t base = node_base + s_base;
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 3);  // look-back done
     const unsigned lt = (1u << lane) - 1u;
     // first occurrences: assign the local id, append to ids, publish in the table
 #pragma unroll
@@ -401,6 +429,7 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
         a.agg_src[edge_base + p0 + k * kBlock + tid] = local;
       }
     }
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 4);  // published
     // repeats: wait for the owner (an earlier edge, in this or an earlier tile) to publish
 #pragma unroll
     for (int k = 0; k < kRankItems; k++) {
@@ -417,13 +446,16 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
   }
 
   // the op's counter_update (:69-82), by the last CTA to finish
+  if (tid == 0) trace_mark(a.trace, tslot, tile, 5);  // thread 0 spins done
   __syncthreads();
   if (tid == 0) {
+    trace_mark(a.trace, tslot, tile, 6);  // all spins done
     __threadfence();
     int32_t done = atomicAdd(&a.hs->rank_done, 1);
     s_last = (done == (int32_t)gridDim.x - 1);
   }
   __syncthreads();
+  if (tid == 0) trace_mark(a.trace, tslot, tile, 7);
   if (s_last && tid == 0) {
     __threadfence();
     volatile int32_t* nc = a.nc;
@@ -577,6 +609,13 @@ extern "C" int lg_sampler_set_table_slots(lg_sampler* s, int64_t slots) {
   return sampler_alloc_table(s, slots);
 }
 
+extern "C" int lg_debug_set_trace(lg_sampler* s, unsigned long long* device_buf) {
+  LG_REQUIRE(s, "null sampler");
+  s->trace = (u64*)device_buf;
+  return 0;
+}
+extern "C" int64_t lg_debug_trace_words(void) { return (int64_t)LG_MAX_HOPS * 2 * kTraceTiles * kTracePhases * 2; }
+
 extern "C" int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant) {
   LG_REQUIRE(s, "null sampler");
   LG_REQUIRE(variant >= LG_GATHER_AUTO && variant <= LG_GATHER_TMA, "gather variant %d", variant);
@@ -705,6 +744,7 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   a.stream_id = stream_id;
   a.k0 = (uint32_t)rng_seed;
   a.k1 = (uint32_t)(rng_seed >> 32);
+  a.trace = s->trace;
 
   if (rng_kind == LG_RNG_MINSTD)
     launch_sample<LG_RNG_MINSTD>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
@@ -724,6 +764,7 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   r.hop = hop;
   r.ids_cap = b->num_ids;
   r.status = s->status;
+  r.trace = s->trace;
   rank_relabel_kernel<<<s->rank_tiles[h], kBlock, 0, st>>>(r);
   LG_LAUNCH_OK();
   return 0;

@@ -44,4 +44,5 @@ struct lg_sampler {
     cudaEvent_t ev;
   } done[4];
   int32_t n_done;
+  u64* trace;  // diagnostics: per-tile phase timestamps (lg_debug_set_trace), nullptr in production
 };
