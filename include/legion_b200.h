@@ -107,12 +107,16 @@ int lg_version(void);
 /* bytes / counts a host needs to size things without guessing */
 int64_t lg_num_ids(int32_t batch_size, const int32_t* fanout, int32_t n_hops); /* engine/server.cu:187-199 */
 
-/* ---- sampler handle: private scratch (dedup table, scan state, global-id frontier) ---- */
+/* ---- sampler handle: private scratch (position map, scan state, global-id frontier) ----
+ * num_nodes sizes the position map: one 32-bit word per vertex, the reference's position_map
+ * (engine/server.cu:224; 4*num_nodes bytes per handle).  Words are claimed by lg_batch_generate /
+ * lg_random_sample and released by lg_io_complete (ClearPosMap, engine/operator_impl.cu:542-548); a batch
+ * that never reaches lg_io_complete is released by the next lg_batch_generate on the same handle. */
 int lg_sampler_create(int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
-                      lg_sampler** out);
+                      int64_t num_nodes, lg_sampler** out);
 int lg_sampler_destroy(lg_sampler* s);
-/* dedup-table slots (power of two) — exposed for tests of the collision path */
-int lg_sampler_set_table_slots(lg_sampler* s, int64_t slots);
+/* full reset of the position map and the sticky status (after an overflow status or an aborted batch) */
+int lg_sampler_reset(lg_sampler* s, lg_stream_t stream);
 int64_t lg_sampler_scratch_bytes(const lg_sampler* s);
 /* data mover used by lg_feature_cache_lookup: LG_GATHER_AUTO / LG_GATHER_LDG / LG_GATHER_TMA */
 int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant);
@@ -172,8 +176,8 @@ int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, const lg_fe
 /* IOSubmit is a no-op in the reference (engine/operator_impl.cu:521-539); kept for API parity. */
 int lg_io_submit(lg_sampler* s, lg_stream_t stream, int32_t op_id, const lg_batch* batch);
 
-/* IOComplete (engine/operator_impl.cu:542-580): train mode only — end-of-batch cleanup
- * (ClearPosMap equivalent) and, when node_hotness != NULL, HotnessMeasure
+/* IOComplete (engine/operator_impl.cu:542-580): end-of-batch cleanup (ClearPosMap: the position-map words
+ * of the batch's vertices are released, in every mode) and, in train mode when node_hotness != NULL, HotnessMeasure
  * (cache/cache_impl.cuh:190-198) plus the running max of unique ids (cache/cache.cu:59-61,
  * written to max_ids, a device int32, may be NULL). */
 int lg_io_complete(lg_sampler* s, lg_stream_t stream, int32_t mode, const lg_batch* batch,

@@ -46,9 +46,9 @@ _PROTOS = {
     "lg_last_error": (C.c_char_p, []),
     "lg_version": (C.c_int, []),
     "lg_num_ids": (C.c_int64, [C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
-    "lg_sampler_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(vp)]),
+    "lg_sampler_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.POINTER(vp)]),
     "lg_sampler_destroy": (C.c_int, [vp]),
-    "lg_sampler_set_table_slots": (C.c_int, [vp, C.c_int64]),
+    "lg_sampler_reset": (C.c_int, [vp, vp]),
     "lg_sampler_scratch_bytes": (C.c_int64, [vp]),
     "lg_sampler_set_gather_variant": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_overlap": (C.c_int, [vp, C.c_int32]),

@@ -8,15 +8,18 @@
 //                       shard / host UVA), per-entry edge count min(deg, fanout), chained scan
 //                       (decoupled look-back) for the canonical edge offsets, with-replacement
 //                       pick (Philox4x32-10 or the reference's minstd stream), edge emission in
-//                       ascending slot order, insert-min of (vertex -> first edge position) into
-//                       the batch dedup table.
-//   rank_relabel_kernel first-occurrence flags -> chained scan -> batch-local ids in first-seen
-//                       order, `ids` append, COO source relabel (construct_graph), the op's
-//                       counter_update done by the last CTA.
+//                       ascending slot order, RED.MIN of (kNewBit | first edge position) into the
+//                       position map word of the sampled vertex.  For hop > 1 it also writes the
+//                       previous hop's agg_src (construct_graph) — it reads those words anyway.
+//   rank_kernel         first-occurrence flags -> scan -> batch-local ids in first-seen order, `ids`
+//                       append, position-map publish, the op's counter_update by the last CTA.
+//   relabel_kernel      last hop only: agg_src[e] = position_map[src] (construct_graph).
 //
-// State that the reference keeps O(N) per GPU (accessed bitmap + position_map, memset / cleared
-// every batch: engine/operator_impl.cu:151,542-548) is an O(batch) open-addressing table of
-// (vertex, local id) words that stays L2-resident.
+// Dedup state: one 32-bit word per vertex (the reference's position_map, engine/server.cu:224) —
+// 180 GB of HBM makes 4 B/vertex cheap even at 1 B vertices.  Unlike the reference there is no
+// accessed-bitmap and no per-batch O(N) memset (engine/operator_impl.cu:151): words are released
+// by an O(batch) pass at the end of the batch (ClearPosMap, :542-548).  Every random access of
+// the sampler is one 4-byte load, store or fire-and-forget RED: no hashing, no probe loops, no CAS.
 #include "common.cuh"
 #include "sampler_state.cuh"
 
@@ -24,13 +27,11 @@ using namespace lg;
 
 namespace {
 
-constexpr u64 kEmpty = 0xFFFFFFFFFFFFFFFFull;
-constexpr uint32_t kNewBit = 0x80000000u;  // value = kNewBit | first edge position while a hop is open
+constexpr uint32_t kPmEmpty = 0xFFFFFFFFu;  // position-map word of a vertex not in the batch
+constexpr uint32_t kNewBit = 0x80000000u;   // kNewBit | first edge position while a hop is open; final local ids are < 2^31
 constexpr int kBlock = 256;
-constexpr int kRankItems = 4;                      // edges per thread in rank_relabel_kernel
-constexpr int kRankTile = kBlock * kRankItems;     // 1024 edges per tile
-static_assert(kRankItems * (kBlock / 32) == 32, "rank tile partial counts must fill one warp");
-constexpr int kSlotUnroll = 4;                     // neighbour reads in flight per thread in sample_hop_kernel
+constexpr int kSlotUnroll = 5;              // neighbour reads in flight per thread in sample_hop_kernel
+constexpr int kAnchor = 1024;               // chained scan: every kAnchor-th tile also publishes its inclusive prefix
 
 // optional per-tile phase timestamps (diagnostics only: lg_debug_set_trace; nullptr in production)
 constexpr int kTraceTiles = 2048, kTracePhases = 8;
@@ -44,67 +45,78 @@ __device__ __forceinline__ void trace_mark(u64* trace, int kernel_slot, int tile
   p[1] = c;
 }
 
-// Insert-min of (key -> val).  The pre-check reads the slot through L1 (ld.ca): popular vertices are sampled
-// thousands of times per batch, and sending every one of those reads to the single L2 slice that owns the
-// slot serialises the whole kernel.  A stale line is harmless: keys never change once written, values only
-// decrease, so a stale value can only make us issue an atomic that turns out to be a no-op — never skip
-// one that was needed (stale >= actual, and we skip only when stale <= val).
-__device__ __forceinline__ void table_insert_min(u64* table, uint32_t mask, int32_t key, uint32_t val) {
-  uint32_t slot = hash32((uint32_t)key) & mask;
-  const u64 packed = ((u64)(uint32_t)key << 32) | val;
-  while (true) {
-    u64 cur = __ldca(table + slot);
-    if (cur == kEmpty) {
-      cur = atomicCAS(table + slot, kEmpty, packed);
-      if (cur == kEmpty) return;
-    }
-    if ((uint32_t)(cur >> 32) == (uint32_t)key) {
-      if ((uint32_t)cur > val) atomicMin(table + slot, packed);
-      return;
-    }
-    slot = (slot + 1) & mask;
-  }
+__device__ __forceinline__ uint32_t ld_ca_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
-// Batched form: the caller has already loaded `cur` = table[slot] for several keys at once (memory-level
-// parallelism across a thread's slots) and, for empty slots, already issued the CAS (`cur` = its return value,
-// `claimed` = the CAS found the slot empty).  Finishes the insert; falls back to linear probing on a collision.
-__device__ __forceinline__ void table_insert_finish(u64* table, uint32_t mask, int32_t key, uint32_t val, uint32_t slot,
-                                                    u64 cur, bool claimed) {
-  if (claimed) return;
-  if ((uint32_t)(cur >> 32) == (uint32_t)key) {
-    if ((uint32_t)cur > val) atomicMin(table + slot, ((u64)(uint32_t)key << 32) | val);
-    return;
-  }
-  // another key owns this slot: continue with the generic probe sequence from the next slot
-  const u64 packed = ((u64)(uint32_t)key << 32) | val;
-  slot = (slot + 1) & mask;
-  while (true) {
-    cur = __ldca(table + slot);
-    if (cur == kEmpty) {
-      cur = atomicCAS(table + slot, kEmpty, packed);
-      if (cur == kEmpty) return;
-    }
-    if ((uint32_t)(cur >> 32) == (uint32_t)key) {
-      if ((uint32_t)cur > val) atomicMin(table + slot, packed);
-      return;
-    }
-    slot = (slot + 1) & mask;
-  }
+__device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// key must be present.  `cached`: probe through L1 — valid when the caller only needs the key/slot or a value
-// that cannot have changed since the kernel started (keys are immutable within a batch).
-template <bool CACHED>
-__device__ __forceinline__ uint32_t table_find(const u64* table, uint32_t mask, int32_t key, u64* word) {
-  uint32_t slot = hash32((uint32_t)key) & mask;
-  while (true) {
-    u64 cur = CACHED ? __ldca(table + slot) : ld_relaxed(table + slot);
-    if ((uint32_t)(cur >> 32) == (uint32_t)key || cur == kEmpty) {
-      *word = cur;
-      return slot;
-    }
-    slot = (slot + 1) & mask;
+// ------------------------------------------------------------------------------------------
+// Exclusive prefix of a tile's aggregate over all earlier tiles, computed by the WHOLE block.
+// Every tile posts (1<<32 | aggregate) once; a tile sums its predecessors' aggregates directly — all loads of a
+// round are in flight together, so the cost is one L2 round trip instead of a chain of dependent look-back
+// windows (measured: 7-10 us per kernel with the classic 32-wide look-back when ~800 tiles start together).
+// To bound the reads for long kernels, tiles (kAnchor*m - 1) also publish their inclusive prefix; a tile sums
+// only the aggregates back to the last anchor boundary and adds that prefix.  Tiles are claimed through an
+// atomic ticket, so every predecessor is already running: the spins cannot deadlock.
+// state: [n_tiles] aggregates followed by [n_tiles / kAnchor + 1] anchor prefixes, zeroed per batch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t block_exclusive_prefix(u64* state, u64* anchors, int tile, int32_t aggregate,
+                                                          int32_t* s_red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) st_relaxed(state + tile, (1ull << 32) | (uint32_t)aggregate);
+  const int a0 = (tile / kAnchor) * kAnchor;  // first tile whose aggregate we add
+  int32_t sum = 0;
+  if (a0 > 0 && tid == 0) {
+    u64 s = ld_relaxed(anchors + a0 / kAnchor);
+    while ((s >> 32) == 0ull) s = ld_relaxed(anchors + a0 / kAnchor);
+    sum = (int32_t)(uint32_t)s;
   }
+  for (int hi = tile - 1; hi >= a0; hi -= kBlock * 4) {
+    u64 s[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int idx = hi - tid - j * kBlock;
+      s[j] = (idx >= a0) ? ld_relaxed(state + idx) : (1ull << 32);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int idx = hi - tid - j * kBlock;
+      while ((s[j] >> 32) == 0ull) s[j] = ld_relaxed(state + idx);
+      sum += (int32_t)(uint32_t)s[j];
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  int32_t excl = 0;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; w++) excl += s_red[w];
+  if (tid == 0 && ((tile + 1) % kAnchor) == 0)
+    st_relaxed(anchors + (tile + 1) / kAnchor, (1ull << 32) | (uint32_t)(excl + aggregate));
+  __syncthreads();  // s_red may be reused by the caller
+  return excl;
+}
+
+// exclusive scan of one int per thread over the block; returns the thread's exclusive prefix, *total = block sum
+__device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* s_red, int32_t* total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int32_t inc = warp_incl_scan(v, lane);
+  if (lane == 31) s_red[warp] = inc;
+  __syncthreads();
+  int32_t before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; w++) {
+    const int32_t x = s_red[w];
+    if (w < warp) before += x;
+    tot += x;
+  }
+  __syncthreads();
+  *total = tot;
+  return before + inc - v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -113,7 +125,7 @@ __device__ __forceinline__ uint32_t table_find(const u64* table, uint32_t mask, 
 __global__ void __launch_bounds__(kBlock) batch_generate_kernel(
     const int32_t* __restrict__ all_ids, const int32_t* __restrict__ all_labels, int32_t total_cap,
     int32_t size, int32_t counter, int32_t hop_num, int32_t* __restrict__ ids, int32_t* __restrict__ labels,
-    int32_t* __restrict__ nc, int32_t* __restrict__ ec, u64* table, uint32_t mask) {
+    int32_t* __restrict__ nc, int32_t* __restrict__ ec, uint32_t* pm) {
   int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x < LG_COUNTER_SLOTS) {
     int t = threadIdx.x;
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(kBlock) batch_generate_kernel(
   int32_t v = all_ids[pos % total_cap];
   ids[idx] = v;
   labels[idx] = all_labels[pos % total_cap];
-  if (v >= 0) table_insert_min(table, mask, v, (uint32_t)idx);  // local index = first position
+  if (v >= 0) red_min_u32(pm + v, (uint32_t)idx);  // position_map (:51): local index = first position
 }
 
 // ------------------------------------------------------------------------------------------
@@ -148,39 +160,41 @@ struct SampleArgs {
   int32_t* agg_dst;
   int32_t* nc;
   int32_t* ec;
-  u64* table;
+  uint32_t* pm;
   u64* tile_state;
+  u64* anchors;
   HopState* hs;
   u64* edge_hot;
-  uint32_t mask;
   int32_t hop;
   int32_t fanout;
+  uint32_t fanout_magic;  // ceil(2^32 / fanout): slot / fanout as one multiply-high (slot < 2^16)
+  int32_t relabel_prev;   // also write the previous hop's agg_src (its construct_graph) from the position map
   uint32_t batch_id, stream_id, k0, k1;
   u64* trace;
 };
 
-template <int TILE_F, int RNG, int INS>
+template <int TILE_F, int RNG>
 __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) {
+  static_assert(TILE_F <= kBlock, "one thread per frontier entry of the tile");
   __shared__ long long s_start[TILE_F];
+  __shared__ const int32_t* s_indices[TILE_F];
   __shared__ int32_t s_deg[TILE_F];
   __shared__ int32_t s_cnt[TILE_F];
   __shared__ int32_t s_off[TILE_F];
   __shared__ int32_t s_flocal[TILE_F];
-  __shared__ const int32_t* s_indices[TILE_F];
-  __shared__ int32_t s_warp[kBlock / 32];
-  __shared__ int32_t s_tile, s_base;
+  __shared__ int32_t s_red[kBlock / 32];
+  __shared__ int32_t s_tile;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(&a.hs->sample_ticket, 1);
-  __syncthreads();
-  const int tile = s_tile;
-  const int tslot = (a.hop - 1) * 2;
-  if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
-
   const bool first_hop = (a.hop == 1);
   const int32_t F = first_hop ? a.nc[1] : a.ec[1];          // :201-206
   const int32_t prev_edge_off = a.ec[0];
   const int32_t edge_base = a.ec[0] + a.ec[1];              // :275
+  __syncthreads();
+  const int tile = s_tile;
+  const int tslot = (a.hop - 1) * 2;
+  if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
   const int n_tiles = (F + TILE_F - 1) / TILE_F;
   if (tile >= n_tiles) {
     if (n_tiles == 0 && tile == 0 && tid == 0) a.ec[2] = 0;
@@ -190,21 +204,18 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
   const int32_t i0 = tile * TILE_F;
 
   // 1. row lookup for the tile's frontier entries
+  int32_t cnt = 0;
   if (tid < TILE_F) {
     int32_t i = i0 + tid;
-    int32_t cnt = 0, deg = 0, fl = 0;
+    int32_t deg = 0, fl = 0;
     long long start = 0;
     const int32_t* ind = a.topo.indices[a.topo.n_parts];
     if (i < F) {
       int32_t v = first_hop ? a.ids[i] : a.frontier_prev[i];
       if (v >= 0) {
-        if (first_hop) {
-          u64 w;
-          table_find<true>(a.table, a.mask, v, &w);
-          fl = (int32_t)(uint32_t)w;
-        } else {
-          fl = a.agg_src[prev_edge_off + i];
-        }
+        // batch-local index of the frontier vertex (position_map, :291-294): final since the previous op
+        fl = (int32_t)ld_ca_u32(a.pm + v);
+        if (a.relabel_prev) a.agg_src[prev_edge_off + i] = fl;  // construct_graph of the previous hop, fused
         int part = a.topo.n_parts;
         long long row = v;
         if (a.topo.directory) {
@@ -229,36 +240,19 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
     s_flocal[tid] = fl;
     s_indices[tid] = ind;
   }
-  __syncthreads();
   if (tid == 0) trace_mark(a.trace, tslot, tile, 1);
 
-  // 2. exclusive scan of the per-entry edge counts inside the tile
-  {
-    int32_t v = (tid < TILE_F) ? s_cnt[tid] : 0;
-    int32_t inc = warp_incl_scan(v, lane);
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      int32_t w = (lane < kBlock / 32) ? s_warp[lane] : 0;
-      int32_t winc = warp_incl_scan(w, lane);
-      if (lane < kBlock / 32) s_warp[lane] = winc - w;
-      int32_t total = __shfl_sync(0xffffffffu, winc, kBlock / 32 - 1);
-      // 3. chained scan across tiles
-      int32_t excl = lookback_exclusive(a.tile_state, tile, total, lane);
-      if (lane == 0) {
-        s_base = excl;
-        if (tile == n_tiles - 1) a.ec[2] = excl + total;  // E_h (:264)
-      }
-    }
-    __syncthreads();
-    if (tid < TILE_F) s_off[tid] = s_warp[warp] + inc - v;
-  }
-  __syncthreads();
-  const int32_t base = s_base;
+  // 2. exclusive scan of the per-entry edge counts inside the tile, 3. prefix over the earlier tiles
+  int32_t total;
+  const int32_t off = block_exclusive_scan(cnt, s_red, &total);
+  if (tid < TILE_F) s_off[tid] = off;
+  const int32_t base = block_exclusive_prefix(a.tile_state, a.anchors, tile, total, s_red);
+  if (tid == 0 && tile == n_tiles - 1) a.ec[2] = base + total;  // E_h (:264)
   if (tid == 0) trace_mark(a.trace, tslot, tile, 2);
 
-  // 4. one thread per slot: pick, emit, insert-min.  kSlotUnroll independent neighbour reads are issued
-  //    back to back before any of them is consumed (the read is a random 4-byte HBM/NVLink/PCIe access).
+  // 4. one thread per slot: pick, emit, min-insert into the position map.  kSlotUnroll independent neighbour
+  //    reads are issued back to back before any of them is consumed (random 4-byte HBM/NVLink/PCIe accesses);
+  //    the position-map update is a fire-and-forget RED, so nothing in this loop waits on a second round trip.
   const int n_slots = TILE_F * c;
   for (int k0 = tid; k0 < n_slots; k0 += kBlock * kSlotUnroll) {
     int32_t w[kSlotUnroll], p[kSlotUnroll], fl[kSlotUnroll];
@@ -267,7 +261,8 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
       const int k = k0 + u * kBlock;
       p[u] = -1;
       if (k < n_slots) {
-        const int t = k / c, j = k - t * c;
+        const int t = (c == 1) ? k : (int)__umulhi((uint32_t)k, a.fanout_magic);
+        const int j = k - t * c;
         if (j < s_cnt[t]) {  // :232  neighbor_offset >= col_size -> none
           const uint32_t slot = (uint32_t)(i0 + t) * (uint32_t)c + (uint32_t)j;
           const int32_t pick =
@@ -278,51 +273,12 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
         }
       }
     }
-    // dedup-table insert-min.  INS 0: one slot after the other; 1: all first probes of the group in flight
-    // together, claims one by one; 2: probes and claims both batched
-    if (INS == 0) {
 #pragma unroll
-      for (int u = 0; u < kSlotUnroll; u++) {
-        if (p[u] >= 0) {
-          a.gid_out[p[u]] = w[u];
-          a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
-          table_insert_min(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u]);
-        }
-      }
-    } else {
-      uint32_t sl[kSlotUnroll];
-      u64 cur[kSlotUnroll];
-#pragma unroll
-      for (int u = 0; u < kSlotUnroll; u++) {
-        if (p[u] >= 0) {
-          a.gid_out[p[u]] = w[u];
-          a.agg_dst[edge_base + p[u]] = fl[u];
-          sl[u] = hash32((uint32_t)w[u]) & a.mask;
-          cur[u] = __ldca(a.table + sl[u]);
-        }
-      }
-      bool claimed[kSlotUnroll];
-      if (INS == 2) {
-#pragma unroll
-        for (int u = 0; u < kSlotUnroll; u++) {
-          claimed[u] = false;
-          if (p[u] >= 0 && cur[u] == kEmpty) {
-            cur[u] = atomicCAS(a.table + sl[u], kEmpty, ((u64)(uint32_t)w[u] << 32) | (kNewBit | (uint32_t)p[u]));
-            claimed[u] = (cur[u] == kEmpty);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kSlotUnroll; u++) {
-        if (p[u] < 0) continue;
-        if (INS == 1) {
-          claimed[u] = false;
-          if (cur[u] == kEmpty) {
-            cur[u] = atomicCAS(a.table + sl[u], kEmpty, ((u64)(uint32_t)w[u] << 32) | (kNewBit | (uint32_t)p[u]));
-            claimed[u] = (cur[u] == kEmpty);
-          }
-        }
-        table_insert_finish(a.table, a.mask, w[u], kNewBit | (uint32_t)p[u], sl[u], cur[u], claimed[u]);
+    for (int u = 0; u < kSlotUnroll; u++) {
+      if (p[u] >= 0) {
+        a.gid_out[p[u]] = w[u];
+        a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
+        red_min_u32(a.pm + w[u], kNewBit | (uint32_t)p[u]);
       }
     }
   }
@@ -334,122 +290,81 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
-// rank_relabel_kernel
+// rank_kernel: first-occurrence flags -> scan -> batch-local ids in first-seen order, `ids` append, publish
 // ------------------------------------------------------------------------------------------
 struct RankArgs {
   const int32_t* gid;  // this hop's sampled sources
   int32_t* ids;
-  int32_t* agg_src;
   int32_t* nc;
   int32_t* ec;
-  u64* table;
+  uint32_t* pm;
   u64* tile_state;
+  u64* anchors;
   HopState* hs;
-  uint32_t mask;
   int32_t hop;
   int32_t ids_cap;
   int32_t* status;
   u64* trace;
 };
 
-__global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) {
-  __shared__ int32_t s_cnt[kRankItems * (kBlock / 32)];
-  __shared__ int32_t s_tile, s_base, s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int ITEMS>
+__global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
+  static_assert(ITEMS % 4 == 0, "edges are loaded as int4");
+  constexpr int TILE = kBlock * ITEMS;
+  __shared__ int32_t s_red[kBlock / 32];
+  __shared__ int32_t s_tile, s_last;
+  const int tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(&a.hs->rank_ticket, 1);
+  const int32_t E = a.ec[2];
+  const int32_t node_base = a.nc[0] + a.nc[1];  // :268
   __syncthreads();
   const int tile = s_tile;
   const int tslot = (a.hop - 1) * 2 + 1;
   if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
-  const int32_t E = a.ec[2];
-  const int32_t node_base = a.nc[0] + a.nc[1];  // :268
-  const int32_t edge_base = a.ec[0] + a.ec[1];
-  const int n_tiles = (E + kRankTile - 1) / kRankTile;
+  const int n_tiles = (E + TILE - 1) / TILE;
 
   if (tile < n_tiles) {
-    const int32_t p0 = tile * kRankTile;
-    int32_t w[kRankItems];
-    uint32_t slot[kRankItems];
-    bool first[kRankItems];
-    unsigned bal[kRankItems];
-    u64 word[kRankItems];
+    const int32_t p0 = tile * TILE + tid * ITEMS;  // ITEMS consecutive edges per thread
+    int32_t w[ITEMS];
+    uint32_t q[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kRankItems; k++) {  // all first probes of the thread's edges in flight together
-      const int32_t p = p0 + k * kBlock + tid;
-      w[k] = (p < E) ? a.gid[p] : -1;
+    for (int k = 0; k < ITEMS; k += 4) {  // the buffer is padded to a multiple of TILE, reads past E are discarded
+      const int4 v = *reinterpret_cast<const int4*>(a.gid + p0 + k);
+      w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
     }
 #pragma unroll
-    for (int k = 0; k < kRankItems; k++) {
-      slot[k] = hash32((uint32_t)w[k]) & a.mask;
-      // L1-cached probe: a line fetched before the owner publishes still holds kNewBit|p_first, one fetched
-      // after holds the final id — neither can equal kNewBit|p for a non-owner, and the owner's own word is
-      // only ever rewritten by the owner itself
-      word[k] = (w[k] >= 0) ? __ldca(a.table + slot[k]) : 0ull;
+    for (int k = 0; k < ITEMS; k++) {
+      // L1-cached: a line fetched before the owner publishes holds kNewBit|p_first, one fetched after holds the
+      // final id — neither can equal kNewBit|p for a non-owner, and an owner's word is only rewritten by itself
+      q[k] = (p0 + k < E) ? ld_ca_u32(a.pm + w[k]) : 0u;
     }
+    uint32_t mask = 0;
 #pragma unroll
-    for (int k = 0; k < kRankItems; k++) {
-      const int32_t p = p0 + k * kBlock + tid;
-      first[k] = false;
-      if (w[k] >= 0) {
-        while ((uint32_t)(word[k] >> 32) != (uint32_t)w[k] && word[k] != kEmpty) {  // collision: next slot
-          slot[k] = (slot[k] + 1) & a.mask;
-          word[k] = __ldca(a.table + slot[k]);
-        }
-        first[k] = ((uint32_t)word[k] == (kNewBit | (uint32_t)p));
-      }
-      bal[k] = __ballot_sync(0xffffffffu, first[k]);
-      if (lane == 0) s_cnt[k * (kBlock / 32) + warp] = __popc(bal[k]);
-    }
-    if (tid == 0) trace_mark(a.trace, tslot, tile, 1);  // warp 0 probes done
-    __syncthreads();
-    if (tid == 0) trace_mark(a.trace, tslot, tile, 2);  // all probes done
-    if (warp == 0) {  // kRankItems * 8 == 32 partial counts, in edge order
-      int32_t v = s_cnt[lane];
-      int32_t inc = warp_incl_scan(v, lane);
-      s_cnt[lane] = inc - v;
-      int32_t total = __shfl_sync(0xffffffffu, inc, 31);
-      int32_t excl = lookback_exclusive(a.tile_state, tile, total, lane);
-      if (lane == 0) {
-        s_base = excl;
-        if (tile == n_tiles - 1) a.hs->new_nodes = excl + total;  // C_h (:263)
-      }
-    }
-    __syncthreads();
-    const int32_t base = node_base + s_base;
-    if (tid == 0) trace_mark(a.trace, tslot, tile, 3);  // look-back done
-    const unsigned lt = (1u << lane) - 1u;
-    // first occurrences: assign the local id, append to ids, publish in the table
+    for (int k = 0; k < ITEMS; k++)
+      if (p0 + k < E && q[k] == (kNewBit | (uint32_t)(p0 + k))) mask |= 1u << k;
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 1);
+    int32_t total;
+    const int32_t mine = block_exclusive_scan(__popc(mask), s_red, &total);
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 2);
+    const int32_t excl = block_exclusive_prefix(a.tile_state, a.anchors, tile, total, s_red);
+    if (tid == 0 && tile == n_tiles - 1) a.hs->new_nodes = excl + total;  // C_h (:263)
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 3);
+    int32_t local = node_base + excl + mine;
 #pragma unroll
-    for (int k = 0; k < kRankItems; k++) {
-      if (first[k]) {
-        int32_t local = base + s_cnt[k * (kBlock / 32) + warp] + __popc(bal[k] & lt);
+    for (int k = 0; k < ITEMS; k++) {
+      if (mask & (1u << k)) {
         if (local < a.ids_cap) a.ids[local] = w[k];  // :270
         else *a.status = 1;
-        st_relaxed(a.table + slot[k], ((u64)(uint32_t)w[k] << 32) | (uint32_t)local);  // position_map :271
-        a.agg_src[edge_base + p0 + k * kBlock + tid] = local;
+        a.pm[w[k]] = (uint32_t)local;  // position_map :271
+        local++;
       }
     }
-    if (tid == 0) trace_mark(a.trace, tslot, tile, 4);  // published
-    // repeats: wait for the owner (an earlier edge, in this or an earlier tile) to publish
-#pragma unroll
-    for (int k = 0; k < kRankItems; k++) {
-      int32_t p = p0 + k * kBlock + tid;
-      if (p < E && !first[k]) {
-        u64 word = ld_relaxed(a.table + slot[k]);
-        while ((uint32_t)word & kNewBit) {  // back off: thousands of repeats of a hub vertex poll the same word
-          __nanosleep(64);
-          word = ld_relaxed(a.table + slot[k]);
-        }
-        a.agg_src[edge_base + p] = (int32_t)(uint32_t)word;  // construct_graph :291,293
-      }
-    }
+    if (tid == 0) trace_mark(a.trace, tslot, tile, 4);
   }
 
   // the op's counter_update (:69-82), by the last CTA to finish
-  if (tid == 0) trace_mark(a.trace, tslot, tile, 5);  // thread 0 spins done
   __syncthreads();
   if (tid == 0) {
-    trace_mark(a.trace, tslot, tile, 6);  // all spins done
     __threadfence();
     int32_t done = atomicAdd(&a.hs->rank_done, 1);
     s_last = (done == (int32_t)gridDim.x - 1);
@@ -472,6 +387,37 @@ __global__ void __launch_bounds__(kBlock) rank_relabel_kernel(const RankArgs a) 
     ec[2] = 0;
     nc[LG_INTRABATCH_CON * 3 + a.hop] = nc0 + C;
     ec[LG_INTRABATCH_CON * 3 + a.hop] = ec0 + E;
+  }
+}
+
+// construct_graph for the sources of the hop just ranked (:283-296): agg_src[e] = position_map[src].  Runs after the
+// rank kernel's counter_update: (ec[0], ec[1]) = (offset, count) of the hop's edges.  For every hop but the last
+// lg_run_batch folds this pass into the next hop's sample kernel (which reads the same words anyway).
+__global__ void __launch_bounds__(kBlock) relabel_kernel(const int32_t* __restrict__ gid, int32_t* __restrict__ agg_src,
+                                                         const int32_t* __restrict__ ec, const uint32_t* pm) {
+  const int32_t off = ec[0], E = ec[1];
+  const int32_t p0 = (blockIdx.x * kBlock + threadIdx.x) * 4;
+  if (p0 >= E) return;
+  const int4 v = *reinterpret_cast<const int4*>(gid + p0);
+  const int32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t q[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) q[k] = (p0 + k < E) ? ld_ca_u32(pm + w[k]) : 0u;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (p0 + k < E) agg_src[off + p0 + k] = (int32_t)q[k];
+}
+
+// ClearPosMap (:542-548): the position-map words of this batch's vertices go back to "not in the batch".
+// O(batch) work; the map itself is O(N) like the reference's, but never memset.
+__global__ void __launch_bounds__(kBlock) pm_clear_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ nc,
+                                                          uint32_t* pm) {
+  int32_t n = nc[LG_INTRABATCH_CON * 2 + 1];
+  const int32_t seeds = nc[LG_INTRABATCH_CON * 3];
+  if (seeds > n) n = seeds;  // before the first hop nc[7] is still 0
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t v = ids[i];
+    if (v >= 0) pm[v] = kPmEmpty;
   }
 }
 
@@ -501,44 +447,36 @@ extern "C" int64_t lg_num_ids(int32_t batch_size, const int32_t* fanout, int32_t
   return tot;
 }
 
-static int64_t next_pow2(int64_t x) {
-  int64_t p = 1;
-  while (p < x) p <<= 1;
-  return p;
-}
-
 static int pick_tile_f(int64_t frontier_max) {
-  // keep >= ~2 waves of CTAs on 148 SMs when the frontier allows it
-  if (frontier_max >= 256ll * kSMs * 2) return 256;
-  if (frontier_max >= 128ll * kSMs * 2) return 128;
+  // a tile is one CTA: prefer many small tiles for short frontiers (latency), 256-entry tiles for long ones
+  if (frontier_max >= 128ll * kSMs * 4) return 256;
+  if (frontier_max >= 64ll * kSMs * 4) return 128;
   if (frontier_max >= 64ll * kSMs) return 64;
   return 32;
 }
-
-static int sampler_alloc_table(lg_sampler* s, int64_t slots) {
-  if (s->table) cudaFree(s->table);
-  s->table = nullptr;
-  s->table_slots = slots;
-  LG_CUDA(cudaMalloc(&s->table, (size_t)slots * sizeof(u64)));
-  LG_CUDA(cudaMemset(s->table, 0xFF, (size_t)slots * sizeof(u64)));
-  return 0;
+static int pick_rank_items(int64_t edges_max) {
+  // all tiles of a hop resident at once when possible (6 CTAs x 148 SMs): 8 edges per thread up to ~1.8 M edges
+  return (edges_max > 4ll * kBlock * kSMs * 5) ? 8 : 4;
 }
 
 extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
-                                 lg_sampler** out) {
+                                 int64_t num_nodes, lg_sampler** out) {
   LG_REQUIRE(out && fanout, "lg_sampler_create: null argument");
   LG_REQUIRE(n_hops >= 1 && n_hops <= LG_MAX_HOPS, "lg_sampler_create: n_hops %d outside [1,%d]", n_hops, LG_MAX_HOPS);
   LG_REQUIRE(max_batch >= 1, "lg_sampler_create: max_batch %d", max_batch);
+  LG_REQUIRE(num_nodes >= 1 && num_nodes < (1ll << 31), "lg_sampler_create: num_nodes %lld outside [1, 2^31)",
+             (long long)num_nodes);
   LG_CUDA(cudaSetDevice(device));
   lg_sampler* s = new lg_sampler();
   memset(s, 0, sizeof(*s));
   s->device = device;
   s->max_batch = max_batch;
   s->n_hops = n_hops;
+  s->num_nodes = num_nodes;
   s->gather_variant = LG_GATHER_AUTO;
   s->slots_per_hop[0] = max_batch;
   for (int h = 0; h < n_hops; h++) {
-    LG_REQUIRE(fanout[h] >= 1, "lg_sampler_create: fanout[%d]=%d", h, fanout[h]);
+    LG_REQUIRE(fanout[h] >= 1 && fanout[h] <= 65535, "lg_sampler_create: fanout[%d]=%d", h, fanout[h]);
     s->fanout[h] = fanout[h];
     s->slots_per_hop[h + 1] = s->slots_per_hop[h] * fanout[h];
   }
@@ -546,20 +484,33 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_REQUIRE(s->num_ids < (1ll << 31), "lg_sampler_create: num_ids %lld does not fit int32", (long long)s->num_ids);
   int64_t smax = s->slots_per_hop[n_hops];
   if (smax < 2ll * max_batch) smax = 2ll * max_batch;  // head of gid[1] doubles as the e2e seed staging area
-  for (int b = 0; b < 2; b++) LG_CUDA(cudaMalloc(&s->gid[b], (size_t)smax * sizeof(int32_t)));
+  smax = (smax + kBlock * 8 - 1) / (kBlock * 8) * (kBlock * 8);  // whole rank tiles: vector loads never leave the buffer
+  for (int b = 0; b < 2; b++) {
+    LG_CUDA(cudaMalloc(&s->gid[b], (size_t)smax * sizeof(int32_t)));
+    LG_CUDA(cudaMemset(s->gid[b], 0, (size_t)smax * sizeof(int32_t)));
+  }
+  // position map: one word per vertex (the reference's position_map, engine/server.cu:224), 0xFFFFFFFF = absent
+  LG_CUDA(cudaMalloc(&s->pm, (size_t)num_nodes * sizeof(uint32_t)));
+  LG_CUDA(cudaMemset(s->pm, 0xFF, (size_t)num_nodes * sizeof(uint32_t)));
   // small per-batch state
   int64_t bytes = sizeof(HopState) * LG_MAX_HOPS;
   bytes = (bytes + 255) & ~255ll;
-  int64_t off_state[2][LG_MAX_HOPS];
+  int64_t off_state[2][LG_MAX_HOPS], off_anchor[2][LG_MAX_HOPS];
   for (int h = 0; h < n_hops; h++) {
     int tf = pick_tile_f(s->slots_per_hop[h]);
     s->sample_tile_f[h] = tf;
     s->sample_tiles[h] = (int32_t)((s->slots_per_hop[h] + tf - 1) / tf);
-    s->rank_tiles[h] = (int32_t)((s->slots_per_hop[h + 1] + kRankTile - 1) / kRankTile);
+    s->rank_items[h] = pick_rank_items(s->slots_per_hop[h + 1]);
+    const int64_t rank_tile = (int64_t)kBlock * s->rank_items[h];
+    s->rank_tiles[h] = (int32_t)((s->slots_per_hop[h + 1] + rank_tile - 1) / rank_tile);
     off_state[0][h] = bytes;
     bytes += (int64_t)s->sample_tiles[h] * 8;
+    off_anchor[0][h] = bytes;
+    bytes += (int64_t)(s->sample_tiles[h] / kAnchor + 2) * 8;
     off_state[1][h] = bytes;
     bytes += (int64_t)s->rank_tiles[h] * 8;
+    off_anchor[1][h] = bytes;
+    bytes += (int64_t)(s->rank_tiles[h] / kAnchor + 2) * 8;
   }
   s->small_bytes = bytes;
   LG_CUDA(cudaMalloc(&s->small, (size_t)bytes));
@@ -567,7 +518,9 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   s->hs = (HopState*)s->small;
   for (int h = 0; h < n_hops; h++) {
     s->sample_state[h] = (u64*)(s->small + off_state[0][h]);
+    s->sample_anchor[h] = (u64*)(s->small + off_anchor[0][h]);
     s->rank_state[h] = (u64*)(s->small + off_state[1][h]);
+    s->rank_anchor[h] = (u64*)(s->small + off_anchor[1][h]);
   }
   LG_CUDA(cudaMalloc(&s->status, sizeof(int32_t)));
   LG_CUDA(cudaMemset(s->status, 0, sizeof(int32_t)));
@@ -577,8 +530,6 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   s->overlap = 1;
   s->fuse_gathers = 1;
-  int rc = sampler_alloc_table(s, next_pow2(s->num_ids + s->num_ids / 2));
-  if (rc) return rc;
   *out = s;
   return 0;
 }
@@ -586,7 +537,7 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
 extern "C" int lg_sampler_destroy(lg_sampler* s) {
   if (!s) return 0;
   cudaSetDevice(s->device);
-  cudaFree(s->table);
+  cudaFree(s->pm);
   cudaFree(s->gid[0]);
   cudaFree(s->gid[1]);
   cudaFree(s->small);
@@ -600,13 +551,12 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   return 0;
 }
 
-extern "C" int lg_sampler_set_table_slots(lg_sampler* s, int64_t slots) {
+extern "C" int lg_sampler_reset(lg_sampler* s, lg_stream_t stream) {
   LG_REQUIRE(s, "null sampler");
-  LG_REQUIRE(slots > s->num_ids && (slots & (slots - 1)) == 0 && slots <= (1ll << 31),
-             "table slots %lld must be a power of two > num_ids %lld", (long long)slots, (long long)s->num_ids);
-  LG_CUDA(cudaSetDevice(s->device));
-  LG_CUDA(cudaDeviceSynchronize());
-  return sampler_alloc_table(s, slots);
+  LG_CUDA(cudaMemsetAsync(s->pm, 0xFF, (size_t)s->num_nodes * sizeof(uint32_t), (cudaStream_t)stream));
+  LG_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int32_t), (cudaStream_t)stream));
+  s->pm_dirty = 0;
+  return 0;
 }
 
 extern "C" int lg_debug_set_trace(lg_sampler* s, unsigned long long* device_buf) {
@@ -671,7 +621,15 @@ extern "C" int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* hos
 
 extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
   if (!s) return 0;
-  return s->table_slots * 8 + 2 * s->slots_per_hop[s->n_hops] * 4 + s->small_bytes + 4;
+  return s->num_nodes * 4 + 2 * s->slots_per_hop[s->n_hops] * 4 + s->small_bytes + 4;
+}
+
+// the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
+static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
+  pm_clear_kernel<<<kSMs * 4, kBlock, 0, st>>>(b->ids, b->node_counter, s->pm);
+  LG_LAUNCH_OK();
+  s->pm_dirty = 0;
+  return 0;
 }
 
 extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32_t* all_ids,
@@ -682,35 +640,93 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   LG_REQUIRE(b->num_ids >= s->num_ids, "lg_batch_generate: batch buffers hold %d ids, need %lld", b->num_ids,
              (long long)s->num_ids);
   cudaStream_t st = (cudaStream_t)stream_;
-  // reset of the per-batch state: dedup table (replaces the O(N) bitmap memset, :151) + scan state
-  LG_CUDA(cudaMemsetAsync(s->table, 0xFF, (size_t)s->table_slots * sizeof(u64), st));
+  // a previous batch that never reached lg_io_complete still owns position-map words: release them first
+  if (s->pm_dirty) {
+    int rc = clear_position_map(s, st, &s->dirty_batch);
+    if (rc) return rc;
+  }
+  // reset of the per-batch scan state (tickets + tile aggregates); the position map needs no reset
+  // (the reference memsets an N/8-byte bitmap here, :151)
   LG_CUDA(cudaMemsetAsync(s->small, 0, (size_t)s->small_bytes, st));
   long long done = (long long)batch_size * ((long long)counter + 1);
   int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
   if (size < 0) size = 0;
   int grid = size > 0 ? (size + kBlock - 1) / kBlock : 1;
   batch_generate_kernel<<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
-                                                 b->labels, b->node_counter, b->edge_counter, s->table,
-                                                 (uint32_t)(s->table_slots - 1));
+                                                 b->labels, b->node_counter, b->edge_counter, s->pm);
   LG_LAUNCH_OK();
+  s->pm_dirty = 1;
+  s->dirty_batch = *b;
   return 0;
 }
 
-template <int RNG, int INS>
-static void launch_sample_ins(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
-  switch (tile_f) {
-    case 256: sample_hop_kernel<256, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
-    case 128: sample_hop_kernel<128, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
-    case 64: sample_hop_kernel<64, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
-    default: sample_hop_kernel<32, RNG, INS><<<grid, kBlock, 0, st>>>(a); break;
-  }
-}
 template <int RNG>
 static void launch_sample(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
-  static const int ins = [] { const char* e = getenv("LG_SAMPLE_INS"); return e ? atoi(e) : 0; }();
-  if (ins == 2) launch_sample_ins<RNG, 2>(tile_f, grid, st, a);
-  else if (ins == 1) launch_sample_ins<RNG, 1>(tile_f, grid, st, a);
-  else launch_sample_ins<RNG, 0>(tile_f, grid, st, a);
+  switch (tile_f) {
+    case 256: sample_hop_kernel<256, RNG><<<grid, kBlock, 0, st>>>(a); break;
+    case 128: sample_hop_kernel<128, RNG><<<grid, kBlock, 0, st>>>(a); break;
+    case 64: sample_hop_kernel<64, RNG><<<grid, kBlock, 0, st>>>(a); break;
+    default: sample_hop_kernel<32, RNG><<<grid, kBlock, 0, st>>>(a); break;
+  }
+}
+
+// one hop: sample + rank (+ the hop's own relabel pass unless the caller folds it into the next hop's sample kernel)
+static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, int32_t hop, int32_t rng_kind,
+                      uint64_t rng_seed, uint32_t batch_id, uint32_t stream_id, const lg_batch* b,
+                      unsigned long long* edge_hotness, bool relabel_prev, bool relabel_own) {
+  const int h = hop - 1;
+  SampleArgs a;
+  a.topo = *topo;
+  a.frontier_prev = s->gid[(h + 1) & 1];
+  a.gid_out = s->gid[h & 1];
+  a.ids = b->ids;
+  a.agg_src = b->agg_src;
+  a.agg_dst = b->agg_dst;
+  a.nc = b->node_counter;
+  a.ec = b->edge_counter;
+  a.pm = s->pm;
+  a.tile_state = s->sample_state[h];
+  a.anchors = s->sample_anchor[h];
+  a.hs = s->hs + h;
+  a.edge_hot = (u64*)edge_hotness;
+  a.hop = hop;
+  a.fanout = s->fanout[h];
+  a.fanout_magic = (uint32_t)(((1ull << 32) + (uint64_t)s->fanout[h] - 1) / (uint64_t)s->fanout[h]);
+  a.relabel_prev = relabel_prev ? 1 : 0;
+  a.batch_id = batch_id;
+  a.stream_id = stream_id;
+  a.k0 = (uint32_t)rng_seed;
+  a.k1 = (uint32_t)(rng_seed >> 32);
+  a.trace = s->trace;
+  if (rng_kind == LG_RNG_MINSTD)
+    launch_sample<LG_RNG_MINSTD>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+  else
+    launch_sample<LG_RNG_PHILOX>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+  LG_LAUNCH_OK();
+  RankArgs r;
+  r.gid = s->gid[h & 1];
+  r.ids = b->ids;
+  r.nc = b->node_counter;
+  r.ec = b->edge_counter;
+  r.pm = s->pm;
+  r.tile_state = s->rank_state[h];
+  r.anchors = s->rank_anchor[h];
+  r.hs = s->hs + h;
+  r.hop = hop;
+  r.ids_cap = b->num_ids;
+  r.status = s->status;
+  r.trace = s->trace;
+  if (s->rank_items[h] == 8)
+    rank_kernel<8><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+  else
+    rank_kernel<4><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+  LG_LAUNCH_OK();
+  if (relabel_own) {
+    const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
+    relabel_kernel<<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, s->pm);
+    LG_LAUNCH_OK();
+  }
+  return 0;
 }
 
 extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_topology* topo, int32_t hop,
@@ -722,52 +738,10 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   LG_REQUIRE(topo->n_parts >= 0 && topo->n_parts <= LG_MAX_DEVICE, "lg_random_sample: n_parts %d", topo->n_parts);
   LG_REQUIRE(topo->indptr[topo->n_parts] && topo->indices[topo->n_parts], "lg_random_sample: full CSR slot is null");
   LG_REQUIRE(!topo->directory || topo->shard_rows > 0, "lg_random_sample: directory without shard_rows");
-  cudaStream_t st = (cudaStream_t)stream_;
-  const int h = hop - 1;
-  SampleArgs a;
-  a.topo = *topo;
-  a.frontier_prev = s->gid[(h + 1) & 1];
-  a.gid_out = s->gid[h & 1];
-  a.ids = b->ids;
-  a.agg_src = b->agg_src;
-  a.agg_dst = b->agg_dst;
-  a.nc = b->node_counter;
-  a.ec = b->edge_counter;
-  a.table = s->table;
-  a.tile_state = s->sample_state[h];
-  a.hs = s->hs + h;
-  a.edge_hot = (u64*)edge_hotness;
-  a.mask = (uint32_t)(s->table_slots - 1);
-  a.hop = hop;
-  a.fanout = s->fanout[h];
-  a.batch_id = batch_id;
-  a.stream_id = stream_id;
-  a.k0 = (uint32_t)rng_seed;
-  a.k1 = (uint32_t)(rng_seed >> 32);
-  a.trace = s->trace;
-
-  if (rng_kind == LG_RNG_MINSTD)
-    launch_sample<LG_RNG_MINSTD>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
-  else
-    launch_sample<LG_RNG_PHILOX>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
-  LG_LAUNCH_OK();
-  RankArgs r;
-  r.gid = s->gid[h & 1];
-  r.ids = b->ids;
-  r.agg_src = b->agg_src;
-  r.nc = b->node_counter;
-  r.ec = b->edge_counter;
-  r.table = s->table;
-  r.tile_state = s->rank_state[h];
-  r.hs = s->hs + h;
-  r.mask = a.mask;
-  r.hop = hop;
-  r.ids_cap = b->num_ids;
-  r.status = s->status;
-  r.trace = s->trace;
-  rank_relabel_kernel<<<s->rank_tiles[h], kBlock, 0, st>>>(r);
-  LG_LAUNCH_OK();
-  return 0;
+  LG_REQUIRE(topo->num_nodes <= s->num_nodes, "lg_random_sample: topology has %lld vertices, sampler was created for %lld",
+             (long long)topo->num_nodes, (long long)s->num_nodes);
+  return sample_hop(s, (cudaStream_t)stream_, topo, hop, rng_kind, rng_seed, batch_id, stream_id, b, edge_hotness,
+                    /*relabel_prev=*/false, /*relabel_own=*/true);
 }
 
 extern "C" int lg_io_submit(lg_sampler*, lg_stream_t, int32_t, const lg_batch*) { return 0; }
@@ -775,19 +749,25 @@ extern "C" int lg_io_submit(lg_sampler*, lg_stream_t, int32_t, const lg_batch*) 
 extern "C" int lg_io_complete(lg_sampler* s, lg_stream_t stream_, int32_t mode, const lg_batch* b,
                               unsigned long long* node_hotness, int32_t* max_ids) {
   LG_REQUIRE(s && b, "lg_io_complete: null argument");
-  if (mode != LG_TRAINMODE) return 0;  // :558
-  if (node_hotness) {
-    hotness_measure_kernel<<<kSMs * 2, kBlock, 0, (cudaStream_t)stream_>>>(b->ids, b->node_counter,
-                                                                          (u64*)node_hotness, max_ids);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (mode == LG_TRAINMODE && node_hotness) {  // :558
+    hotness_measure_kernel<<<kSMs * 2, kBlock, 0, st>>>(b->ids, b->node_counter, (u64*)node_hotness, max_ids);
     LG_LAUNCH_OK();
   }
-  return 0;
+  // ClearPosMap: the reference clears in train mode only (its bitmap makes stale entries harmless in the
+  // other modes); the position map is the only dedup state here, so it is released in every mode
+  return clear_position_map(s, st, b);
 }
 
 extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
                             const lg_feature_cache* cache, const lg_batch_params* p, const lg_batch* b,
                             unsigned long long* tier_rows) {
   LG_REQUIRE(s && topo && p && b, "lg_run_batch: null argument");
+  LG_REQUIRE(p->rng_kind == LG_RNG_MINSTD || p->rng_kind == LG_RNG_PHILOX, "lg_run_batch: rng_kind %d", p->rng_kind);
+  LG_REQUIRE(topo->n_parts >= 0 && topo->n_parts <= LG_MAX_DEVICE && topo->indptr[topo->n_parts] &&
+                 topo->indices[topo->n_parts], "lg_run_batch: bad topology descriptor");
+  LG_REQUIRE(topo->num_nodes <= s->num_nodes, "lg_run_batch: topology has %lld vertices, sampler was created for %lld",
+             (long long)topo->num_nodes, (long long)s->num_nodes);
   cudaStream_t main_st = (cudaStream_t)stream;
   const bool fork = cache && s->overlap;
   const bool pipelined = cache && s->overlap == 2;
@@ -809,7 +789,9 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
   int first_pending = 0;  // first hop whose rows have not been gathered yet
   for (int hop = 0; hop <= s->n_hops; hop++) {
     if (hop > 0) {
-      rc = lg_random_sample(s, stream, topo, hop, p->rng_kind, p->rng_seed, p->batch_id, p->stream_id, b, nullptr);
+      // the relabel pass of hop h rides in the sample kernel of hop h+1; only the last hop runs its own
+      rc = sample_hop(s, main_st, topo, hop, p->rng_kind, p->rng_seed, p->batch_id, p->stream_id, b, nullptr,
+                      /*relabel_prev=*/hop > 1, /*relabel_own=*/hop == s->n_hops);
       if (rc) return rc;
     }
     if (!cache) continue;

@@ -17,14 +17,20 @@ struct lg_sampler {
   int32_t fanout[LG_MAX_HOPS];
   int64_t slots_per_hop[LG_MAX_HOPS + 1];  // S_0 = batch, S_h = S_{h-1} * fanout_h
   int64_t num_ids;
-  int64_t table_slots;
-  u64* table;            // dedup table: (vertex << 32) | local id, 0xFF..F = empty
+  int64_t num_nodes;
+  uint32_t* pm;          // position map [num_nodes]: 0xFFFFFFFF absent, kNewBit|edge position while a hop is open,
+                         // else the batch-local id (engine/server.cu:224 position_map)
+  int32_t pm_dirty;      // a batch was generated and its words not yet released (lg_io_complete)
+  lg_batch dirty_batch;
   int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)
   uint8_t* small;        // memset-per-batch region: HopState[hops] + chained-scan tile states
   int64_t small_bytes;
   HopState* hs;
   u64* sample_state[LG_MAX_HOPS];
   u64* rank_state[LG_MAX_HOPS];
+  u64* sample_anchor[LG_MAX_HOPS];
+  u64* rank_anchor[LG_MAX_HOPS];
+  int32_t rank_items[LG_MAX_HOPS];  // edges per thread of the hop's rank kernel
   int32_t sample_tiles[LG_MAX_HOPS];
   int32_t sample_tile_f[LG_MAX_HOPS];
   int32_t rank_tiles[LG_MAX_HOPS];

@@ -157,7 +157,7 @@ class DataPath:
         fo = (C.c_int32 * self.hops)(*self.fanout)
         self.num_ids = int(self.L.lg_num_ids(self.max_batch, fo, self.hops))
         h = C.c_void_p()
-        check(self.L.lg_sampler_create(self.device, self.max_batch, fo, self.hops, C.byref(h)))
+        check(self.L.lg_sampler_create(self.device, self.max_batch, fo, self.hops, self.N, C.byref(h)))
         self.sampler = h
         self.topo = Topology()
         self.cache = FeatureCache()

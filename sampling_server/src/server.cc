@@ -134,7 +134,7 @@ class GPURunner : public Runner {
     int max_batch = batch_size;
     for (int m : {VALIDMODE, TESTMODE})
       if (env->GetCurrentBatchsize(local_dev_id_, m) > max_batch) max_batch = env->GetCurrentBatchsize(local_dev_id_, m);
-    LGCHECK(lg_sampler_create(local_dev_id_, max_batch, params->fanout.data(), hop_num, &memorypool_->sampler));
+    LGCHECK(lg_sampler_create(local_dev_id_, max_batch, params->fanout.data(), hop_num, feature->TotalNodeNum(), &memorypool_->sampler));
     if (max_batch > batch_size) num_ids_ = (int32_t)lg_num_ids(max_batch, params->fanout.data(), hop_num);
     if (const char* e = std::getenv("LEGION_RNG")) memorypool_->rng_kind = std::strcmp(e, "minstd") == 0 ? LG_RNG_MINSTD : LG_RNG_PHILOX;
     if (const char* e = std::getenv("LEGION_SEED")) memorypool_->rng_seed = std::strtoull(e, nullptr, 0);

@@ -45,7 +45,7 @@ def test_host_only_entry_points():
     assert L.lg_version() >= 100
     # argument validation happens before any CUDA call
     h = ctypes.c_void_p()
-    assert L.lg_sampler_create(0, 8000, fo, 9, ctypes.byref(h)) != 0
+    assert L.lg_sampler_create(0, 8000, fo, 9, 1000, ctypes.byref(h)) != 0
     assert b"n_hops" in L.lg_last_error()
 
 
