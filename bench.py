@@ -32,6 +32,7 @@ WORKLOADS = {
     "products": ("products", [25, 10], 8000, 20000, True),     # BASELINE.json configs[1] (default)
     "paper100m": ("paper100m", [25, 10], 8000, 20000, False),  # configs[2] shape
     "ukunion": ("ukunion", [25, 10], 8000, 20000, False),      # configs[3] shape: the metric's named graph
+    "clueweb": ("clueweb", [15, 10, 5], 8000, 20000, False),   # configs[4] shape: GCN 3-hop, topology in host UVA
 }
 
 
@@ -196,8 +197,30 @@ def run_ours(args):
             f"train_steps={train_steps} setup {time.time() - t0:.1f}s")
 
     dp = DataPath(local, fanout, B, N, D, rank=rank, world=world)
+    topo_host = args.topo == "host"
+    host_keep = []
+    if topo_host:
+        # full CSR in cudaHostAllocMapped memory, read by the sampler through UVA (storage/storage_management.cu:100-115,
+        # engine/operator_impl.cu:224-243); the device copy only feeds presampling/placement and is dropped afterwards
+        from legion_b200.runner import MappedHostBuffer
+        h_ip, h_ix = MappedHostBuffer((N + 1) * 8), MappedHostBuffer(max(E, 1) * 4)
+        capi.check(dp.L.lg_memcpy_d2h(C.c_void_p(h_ip.host_ptr), C.c_void_p(ip.data_ptr()), (N + 1) * 8, dp._stream()))
+        capi.check(dp.L.lg_memcpy_d2h(C.c_void_p(h_ix.host_ptr), C.c_void_p(ix.data_ptr()), E * 4, dp._stream()))
+        torch.cuda.synchronize()
+        host_keep += [h_ip, h_ix]
     dp.set_full_graph(ip.data_ptr(), ix.data_ptr(), keep=[ip, ix])  # topology replicated in each GPU's HBM
-    if feat is not None:
+    feat_host = args.cache_ratio < 1.0
+    if feat_host:
+        # backing matrix in pinned host memory (cache/cache_impl.cuh:262-266 reads misses through UVA)
+        from legion_b200.runner import MappedHostBuffer
+        h_feat = MappedHostBuffer(N * D * 4)
+        for r0 in range(0, N, 1 << 22):  # generated by the device straight into the mapped allocation
+            capi.check(dp.L.lg_synth_features(dp._stream(), r0, min(1 << 22, N - r0), D, SEED,
+                                              C.c_void_p(h_feat.dev_ptr + r0 * D * 4)))
+        torch.cuda.synchronize()
+        host_keep.append(h_feat)
+        dp.set_backing_features(h_feat.dev_ptr, keep=[h_feat])
+    elif feat is not None:
         dp.set_backing_features(feat.data_ptr(), keep=[feat])
     dp.set_overlap(args.overlap)
     dp.set_gather_variant({"auto": capi.GATHER_AUTO, "ldg": capi.GATHER_LDG, "tma": capi.GATHER_TMA}[args.gather])
@@ -226,11 +249,28 @@ def run_ours(args):
         while kg < world and table_bytes / kg > args.cache_gb * 1e9:
             kg *= 2
     assert world % kg == 0, "world size must be a multiple of Kg"
-    cap = (N + kg - 1) // kg  # whole table cached across the clique
-    if feat is not None:
+    # rows cached across the clique: the whole table, or its hottest --cache-ratio fraction (misses -> pinned host)
+    cap = (int(N * min(args.cache_ratio, 1.0)) + kg - 1) // kg
+    cap = max(cap, 1)
+    if feat is not None and not feat_host:
         dp.build_feature_cache(order, cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
-    else:  # paper-scale shapes: shards generated in place, no [N x D] matrix in vertex order anywhere
-        dp.build_feature_cache_synth(order, cap, SEED, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
+    else:  # shards generated in place (paper-scale shapes: no [N x D] matrix in vertex order in HBM)
+        dp.build_feature_cache_synth(order, cap, SEED, kg=kg, j=rank % kg, dist=dist if world > 1 else None,
+                                     keep_backing=feat_host)
+    topo_cap = 0
+    if topo_host:
+        # hot-vertex topology cache in HBM (GraphCache, storage/graph_storage.cu:76-111), ranked by the presampled
+        # edge hotness (QT, cache/cache.cu:420-440); everything else is read from the host CSR over PCIe
+        if world > 1:
+            dist.all_reduce(eh)
+        if args.topo_cache_ratio > 0:
+            order_t, _ = dp.rank_hotness(eh)
+            topo_cap = max(1, (int(N * min(args.topo_cache_ratio, 1.0)) + kg - 1) // kg)
+            dp.build_topology_cache(order_t, topo_cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
+            del order_t
+        dp.repoint_full_graph(h_ip.dev_ptr, h_ix.dev_ptr, drop=[ip, ix])
+        np_ip, np_ix = h_ip.numpy(np.int64, (N + 1,)), h_ix.numpy(np.int32, (E,))
+        del ip, ix
     max_ids = int(mx.item())
     feature_rows = min(dp.num_ids, int(max_ids * 1.2) + 1)  # engine/server.cu:277
     del scratch, eh, nh
@@ -441,9 +481,12 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 ids / fp32 rows moved bit-exact",
             "data": "synthetic",
-            "config": {"workload": f"{shape['name']}-shaped synthetic graph fully HBM-cached (BASELINE.json " + {"products": "configs[1]", "paper100m": "configs[2] shape", "ukunion": "configs[3] shape, 128-d"}[shape["name"]] + ")",
+            "config": {"workload": f"{shape['name']}-shaped synthetic graph (BASELINE.json " + {"products": "configs[1]", "paper100m": "configs[2] shape", "ukunion": "configs[3] shape, 128-d", "clueweb": "configs[4] shape"}[shape["name"]] + ")",
                        "num_nodes": N, "num_edges": E, "feature_dim": D, "fanout": fanout, "batch": B,
-                       "scale": args.scale, "cache": f"Kc={world // kg},Kg={kg}: feature table interleaved by hotness rank over {kg} GPU(s) per clique; topology replicated in HBM",
+                       "scale": args.scale, "cache": f"Kc={world // kg},Kg={kg}: feature table interleaved by hotness rank over {kg} GPU(s) per clique"
+                                + (f", hottest {args.cache_ratio:.3f} of the rows in HBM ({cap} rows/GPU), the rest in pinned host memory (UVA)" if feat_host else ", fully HBM-cached")
+                                + (f"; topology in pinned host memory (UVA) with the hottest {args.topo_cache_ratio:.3f} of the adjacency lists cached in HBM ({topo_cap} rows/GPU)" if topo_host else "; topology replicated in HBM"),
+                       "feature_cache_ratio": args.cache_ratio, "topology": args.topo, "topology_cache_ratio": args.topo_cache_ratio if topo_host else None,
                        "rng": "philox4x32-10", "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
                        "l2": "working set (topology + features + per-batch output, >1.5 GB) exceeds the 126 MB L2; every step samples different seeds"},
             "e2e": {"value": seeds / t_e2e, "unit": "seeds/s", "h2d_bytes_per_step": 2 * 4 * B, "d2h_bytes_per_step": 128,
@@ -466,14 +509,17 @@ def run_ours(args):
             "tier_rows": {"local": int(tiers[0]), "peer": int(tiers[1]), "host_or_backing": int(tiers[2])},
             "clocks": clk,
         }
-        out["gpu_launches"] = args.steps * (1 + n_gather_launches + 2 * H)  # batch_generate + gathers + (sample, rank) per hop
+        # batch_generate + (sample, rank) per hop + the last hop's relabel + pm_clear + gathers (memsets/copies not counted)
+        out["gpu_launches"] = args.steps * (1 + 2 * H + 1 + 1 + n_gather_launches)
         tr = recorded_traffic()
         if tr:
             out["roofline"]["traffic"] = tr.get("traffic_bytes_per_step")
             out["roofline"]["traffic_source"] = tr.get("source")
     # --- CPU baseline beside it (rank 0, N=1 only) ---
     if rank == 0 and world == 1 and not args.no_cpu_baseline and feat is not None:
-        out["cpu_baseline"] = cpu_arm(shape, ip.cpu().numpy(), ix.cpu().numpy(), feat.cpu().numpy(), my_train, steps=args.cpu_steps,
+        if not topo_host:
+            np_ip, np_ix = ip.cpu().numpy(), ix.cpu().numpy()
+        out["cpu_baseline"] = cpu_arm(shape, np_ip, np_ix, feat.cpu().numpy(), my_train, steps=args.cpu_steps,
                                       warmup=1)["cpu_baseline"]
     if world > 1:
         dist.barrier()
@@ -561,6 +607,13 @@ def main():
                     help="gather launches per batch: 0 one per lookup op, 1 seeds ride with hop 1, 2 single gather")
     ap.add_argument("--kg", type=int, default=0, help="GPUs sharing one partitioned cache (0 = auto by capacity)")
     ap.add_argument("--cache-gb", type=float, default=100.0, help="per-GPU feature-cache budget used by --kg auto")
+    ap.add_argument("--cache-ratio", type=float, default=1.0,
+                    help="fraction of the feature rows cached in HBM across the clique; < 1 puts the backing matrix in "
+                         "pinned host memory and misses are read over PCIe (UVA)")
+    ap.add_argument("--topo", default="hbm", choices=["hbm", "host"],
+                    help="where the full CSR lives: replicated in HBM, or pinned host memory read through UVA")
+    ap.add_argument("--topo-cache-ratio", type=float, default=0.0,
+                    help="with --topo host: fraction of the vertices whose adjacency lists are cached in HBM")
     ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (own scratch + stream each)")
     ap.add_argument("--overlap", type=int, default=2, choices=[0, 1, 2],
                     help="0 one stream; 1 gathers overlap the next hop; 2 pipelined across the two batch slots")

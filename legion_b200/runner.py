@@ -189,6 +189,14 @@ class DataPath:
         self.topo = t
         self.topo_directory = directory
 
+    def repoint_full_graph(self, indptr_ptr, indices_ptr, drop=()):
+        """slot P now points at another copy of the full CSR (e.g. the pinned-host one once the HBM copy used for
+        presampling and the cache fill is released); the cached shards and the directory stay"""
+        self._full = (int(indptr_ptr), int(indices_ptr))
+        t = self.topo
+        t.indptr[t.n_parts], t.indices[t.n_parts] = self._full
+        self._keep = [k for k in self._keep if not any(k is d for d in drop)]
+
     def set_backing_features(self, ptr, keep=()):
         self._backing = int(ptr)
         self._keep.extend(keep)
@@ -243,7 +251,7 @@ class DataPath:
         self.feat_shard = raw
         return directory
 
-    def build_feature_cache_synth(self, order, cap, seed, kg=1, j=0, dist=None):
+    def build_feature_cache_synth(self, order, cap, seed, kg=1, j=0, dist=None, keep_backing=False):
         """as build_feature_cache, but the shard is generated in place from the synthetic feature function
         (include/legion_b200_synth.h): no [N x D] backing matrix exists anywhere (paper-scale shapes)"""
         st = self._stream()
@@ -260,7 +268,8 @@ class DataPath:
         if kg > 1:
             shard_ptrs = self._exchange(raw, cap * self.dim * 4, kg, j, dist)
         self.local_part = j
-        self._backing = 0
+        if not keep_backing:
+            self._backing = 0
         self._set_cache(shard_ptrs, directory, cap)
         self.feat_shard = raw
         return directory
