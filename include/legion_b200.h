@@ -145,7 +145,7 @@ int64_t lg_debug_trace_words(void);
 
 /* BatchGenerate (engine/operator_impl.cu:27-55,92-172): seeds of batch `counter` =
  * all_ids[batch_size*counter ...], -1 past total_cap; labels; counters reset + op-0 update;
- * seeds enter the dedup table with local index = position. */
+ * seeds enter the position map with local index = position. */
 int lg_batch_generate(lg_sampler* s, lg_stream_t stream, const int32_t* all_ids,
                       const int32_t* all_labels, int32_t total_cap, int32_t batch_size,
                       int32_t counter, const lg_batch* batch);
