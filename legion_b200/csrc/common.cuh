@@ -7,6 +7,7 @@
 #include "../../include/legion_b200.h"
 
 int lg_set_error(const char* fmt, ...);
+int lg_l2_hints();  // LG_L2_HINTS bitmask (see the L2 eviction-priority helpers below)
 
 #define LG_CUDA(expr)                                                                       \
   do {                                                                                      \
@@ -80,6 +81,44 @@ __device__ __forceinline__ u64 ld_relaxed(const u64* p) {
 }
 __device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- L2 eviction priorities (createpolicy + .L2::cache_hint).  The small random-access arrays of the sampler
+//      (position map, directories, indptr) are worth keeping in the 126 MB L2 while the gather streams ~0.8 GB per
+//      batch through it; the gather's rows and output have no reuse.  kind: 0 normal, 1 evict_last, 2 evict_first.
+//      LG_L2_HINTS (environment, read once) selects which accesses carry a hint:
+//      bit 0 gather row loads evict_first, bit 1 gather output stores evict_first, bit 2 sampler arrays + feature
+//      directory evict_last, bit 3 neighbour (indices) reads evict_first. ----
+__device__ __forceinline__ u64 l2_policy(int kind) {
+  u64 p;
+  if (kind == 1)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint32_t ld_ca_u32_hint(const uint32_t* p, u64 pol) {
+  uint32_t v;
+  asm volatile("ld.global.ca.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int32_t ld_nc_s32_hint(const int32_t* p, u64 pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ long long ld_nc_s64_hint(const int64_t* p, u64 pol) {
+  long long v;
+  asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_u32_hint(uint32_t* p, uint32_t v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_min_u32_hint(uint32_t* p, uint32_t v, u64 pol) {
+  asm volatile("red.relaxed.gpu.global.min.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
 __device__ __forceinline__ uint32_t hash32(uint32_t k) {  // murmur3 fmix32

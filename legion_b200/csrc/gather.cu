@@ -31,6 +31,7 @@ struct GatherArgs {
   int32_t local_part;
   u64* tier;           // [3] local / peer / miss rows, may be null
   int32_t* status;
+  int32_t l2;          // lg_l2_hints()
 };
 
 __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int64_t* cnt) {
@@ -170,13 +171,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, u64 pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "l"(pol)
                : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, u64 pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes),
+               "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   int64_t off, cnt;
   row_range(a, &off, &cnt);
   const int lane = threadIdx.x;
+  const u64 pol_ld = l2_policy((a.l2 & 1) ? 2 : 0), pol_st = l2_policy((a.l2 & 2) ? 2 : 0), keep = l2_policy((a.l2 & 4) ? 1 : 0);
   const uint32_t row_bytes = (uint32_t)a.cache.dim * 4u;
   const uint32_t stage_bytes = row_bytes * kTmaRows;
   const int64_t n_tiles = (cnt + kTmaRows - 1) / kTmaRows;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   };
   auto load_loc = [&](int32_t id) -> int32_t {
     if (id < 0 || !a.cache.directory || id >= a.cache.num_nodes) return LG_CACHEMISS_FLAG;
-    return a.cache.directory[id];
+    return ld_nc_s32_hint(a.cache.directory + id, keep);
   };
   auto form_ptr = [&](int32_t id, int32_t gidx) -> const float* {
     if (id < 0) return nullptr;  // -1 padding / out of range rows are skipped (cache_impl.cuh:263-264)
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
         mbar_expect_tx(bar, row_bytes * (uint32_t)__popc(valid));
       }
       __syncwarp();
-      if (src) bulk_g2s(smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), src, row_bytes, bar);
+      if (src) bulk_g2s(smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), src, row_bytes, bar, pol_ld);
     }
     id0 = id1;
     id1 = id2;
@@ -281,10 +284,10 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
       if (valid == want) {
         // every row of the tile is present: the destination rows are contiguous -> ONE bulk store
         if (lane == 0) bulk_s2g(a.dst + row0 * a.cache.dim, smem_u32(smem + (size_t)s * stage_bytes),
-                                row_bytes * (uint32_t)rows_here);
+                                row_bytes * (uint32_t)rows_here, pol_st);
       } else if (valid & (1u << lane)) {  // holes (-1 padded seeds): row-wise stores
         bulk_s2g(a.dst + (row0 + lane) * a.cache.dim,
-                 smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), row_bytes);
+                 smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), row_bytes, pol_st);
       }
       bulk_commit();  // every lane commits one (possibly empty) group per drained tile
       __syncwarp();
@@ -297,14 +300,15 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
 // tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {4,8}, LG_TMA_STAGES {3,4,6},
 // LG_LDG_CTAS resident CTAs per SM assumed when sizing the LDG grid
 struct Tune {
-  int ldg_r, tma_stages, ldg_ctas;
+  int ldg_r, tma_stages, ldg_ctas, tma_ctas;
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 3, 8};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
+    Tune x{8, 3, 8, 4};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
     if (const char* e = getenv("LG_LDG_CTAS")) x.ldg_ctas = atoi(e);
+    if (const char* e = getenv("LG_TMA_CTAS")) x.tma_ctas = atoi(e);  // cap on resident gather CTAs per SM (smem left for the sampler)
     return x;
   }();
   return t;
@@ -315,7 +319,7 @@ int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
   const size_t smem = (size_t)a.cache.dim * 4 * kTmaRows * STAGES;
   LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (ctas_per_sm > 16) ctas_per_sm = 16;
+  if (ctas_per_sm > tune().tma_ctas) ctas_per_sm = tune().tma_ctas;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   int64_t tiles = (max_rows + kTmaRows - 1) / kTmaRows;
   int64_t grid = (int64_t)kSMs * ctas_per_sm;
@@ -399,6 +403,7 @@ extern "C" int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, 
   a.local_part = local_part;
   a.tier = (u64*)tier_rows;
   a.status = s->status;
+  a.l2 = lg_l2_hints();
   LG_REQUIRE(a.hop <= s->n_hops, "lg_feature_cache_lookup: op_id %d beyond %d hops", op_id, s->n_hops);
   int64_t max_rows = 0;
   for (int h = first_hop; h <= a.hop; h++) max_rows += s->slots_per_hop[h];
@@ -427,5 +432,6 @@ extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache,
   a.local_part = local_part;
   a.tier = (u64*)tier_rows;
   a.status = dummy_status;
+  a.l2 = lg_l2_hints();
   return launch_gather((cudaStream_t)stream, a, variant, n);
 }

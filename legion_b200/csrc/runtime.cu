@@ -5,8 +5,17 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
+
+int lg_l2_hints() {  // see common.cuh; read once
+  static int v = [] {
+    const char* e = getenv("LG_L2_HINTS");
+    return e ? atoi(e) : 4;  // default: keep the small random-access arrays (profiles/r01b_l2_hints.md)
+  }();
+  return v;
+}
 
 int lg_set_error(const char* fmt, ...) {
   va_list ap;

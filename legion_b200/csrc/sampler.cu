@@ -15,11 +15,18 @@
 //                       append, position-map publish, the op's counter_update by the last CTA.
 //   relabel_kernel      last hop only: agg_src[e] = position_map[src] (construct_graph).
 //
-// Dedup state: one 32-bit word per vertex (the reference's position_map, engine/server.cu:224) —
-// 180 GB of HBM makes 4 B/vertex cheap even at 1 B vertices.  Unlike the reference there is no
-// accessed-bitmap and no per-batch O(N) memset (engine/operator_impl.cu:151): words are released
-// by an O(batch) pass at the end of the batch (ClearPosMap, :542-548).  Every random access of
-// the sampler is one 4-byte load, store or fire-and-forget RED: no hashing, no probe loops, no CAS.
+// Dedup state ("position map": vertex -> kNewBit | first edge position while a hop is open, batch-local id
+// afterwards), two layouts chosen per handle by the size of the graph (lg_sampler_create):
+//   DENSE   one 32-bit word per vertex (the reference's position_map, engine/server.cu:224).  Every access is one
+//           4-byte load, store or fire-and-forget RED.MIN: no hashing, no probes.  No accessed-bitmap and no
+//           per-batch O(N) memset (engine/operator_impl.cu:151): words are released by an O(batch) pass at the
+//           end of the batch (ClearPosMap, :542-548).  Best while 4N bytes stay L2-resident (products: 10 MB).
+//   HASHED  O(batch) open-addressing table of (vertex << 32 | value) words, 2^k >= 1.5 x num_ids slots (32 MB for
+//           B=8000, [25,10]), L2-resident whatever N is.  With a 534 MB (UK-Union) or 3.8 GB (Clueweb) dense map
+//           every one of the ~10 M map accesses of a batch is a random DRAM access; the table keeps them in L2.
+//           Insert-min is ONE returning atomicMin per probe on the packed word: an empty slot (all ones) or the
+//           same key take the minimum directly; a larger resident key is displaced and carried to the next slot
+//           (linear probing, no CAS, no pre-read).  The table is re-initialised by one 32 MB memset per batch.
 #include "common.cuh"
 #include "sampler_state.cuh"
 
@@ -45,13 +52,67 @@ __device__ __forceinline__ void trace_mark(u64* trace, int kernel_slot, int tile
   p[1] = c;
 }
 
-__device__ __forceinline__ uint32_t ld_ca_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p));
+
+// ------------------------------------------------------------------------------------------
+// Position map, dense or hashed (see the header comment).  kPmEmpty is "not in the batch" in both layouts
+// (the low word of an empty table slot is all ones too).
+// ------------------------------------------------------------------------------------------
+constexpr u64 kSlotEmpty = 0xFFFFFFFFFFFFFFFFull;
+struct DedupMap {
+  uint32_t* pm;   // DENSE: [num_nodes]
+  u64* table;     // HASHED: [mask + 1]
+  uint32_t mask;
+};
+__device__ __forceinline__ u64 atom_min_u64_hint(u64* p, u64 v, u64 pol) {
+  u64 old;
+  asm volatile("atom.relaxed.gpu.global.min.L2::cache_hint.u64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(v), "l"(pol) : "memory");
+  return old;
+}
+__device__ __forceinline__ u64 ld_ca_u64_hint(const u64* p, u64 pol) {
+  u64 v;
+  asm volatile("ld.global.ca.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
   return v;
 }
-__device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
-  asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_u64_hint(u64* p, u64 v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ u64 map_pack(uint32_t v, uint32_t val) { return ((u64)v << 32) | val; }
+__device__ __forceinline__ uint32_t map_home(const DedupMap& m, uint32_t v) { return hash32(v) & m.mask; }
+// HASHED insert-min, continued after the first probe (`old` = what the atomicMin at `slot` returned)
+__device__ __forceinline__ void table_insert_finish(const DedupMap& m, uint32_t slot, u64 carry, u64 old, u64 pol) {
+  while (true) {
+    if (old == kSlotEmpty || (uint32_t)(old >> 32) == (uint32_t)(carry >> 32)) return;  // claimed / merged
+    if (old > carry) carry = old;  // a larger key lived here: our word took its place, it moves on
+    slot = (slot + 1) & m.mask;
+    old = atom_min_u64_hint(m.table + slot, carry, pol);
+  }
+}
+template <bool HASHED>
+__device__ __forceinline__ void map_insert_min(const DedupMap& m, uint32_t v, uint32_t val, u64 pol) {
+  if (HASHED) {
+    const uint32_t slot = map_home(m, v);
+    const u64 carry = map_pack(v, val);
+    table_insert_finish(m, slot, carry, atom_min_u64_hint(m.table + slot, carry, pol), pol);
+  } else {
+    red_min_u32_hint(m.pm + v, val, pol);
+  }
+}
+// HASHED lookup, continued after the first probe; returns the value (kPmEmpty if absent), *slot = where it lives
+__device__ __forceinline__ uint32_t table_find_finish(const DedupMap& m, uint32_t v, uint32_t* slot, u64 cur, u64 pol) {
+  while ((uint32_t)(cur >> 32) != v && cur != kSlotEmpty) {
+    *slot = (*slot + 1) & m.mask;
+    cur = ld_ca_u64_hint(m.table + *slot, pol);
+  }
+  return (uint32_t)cur;
+}
+// L1-cached (see the rank kernel for why a stale line is harmless)
+template <bool HASHED>
+__device__ __forceinline__ uint32_t map_lookup(const DedupMap& m, uint32_t v, u64 pol) {
+  if (HASHED) {
+    uint32_t slot = map_home(m, v);
+    return table_find_finish(m, v, &slot, ld_ca_u64_hint(m.table + slot, pol), pol);
+  }
+  return ld_ca_u32_hint(m.pm + v, pol);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -122,10 +183,12 @@ __device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* s_re
 // ------------------------------------------------------------------------------------------
 // batch_generate + op-0 counter_update (engine/operator_impl.cu:27-89,159-165)
 // ------------------------------------------------------------------------------------------
+template <bool HASHED>
 __global__ void __launch_bounds__(kBlock) batch_generate_kernel(
     const int32_t* __restrict__ all_ids, const int32_t* __restrict__ all_labels, int32_t total_cap,
     int32_t size, int32_t counter, int32_t hop_num, int32_t* __restrict__ ids, int32_t* __restrict__ labels,
-    int32_t* __restrict__ nc, int32_t* __restrict__ ec, uint32_t* pm) {
+    int32_t* __restrict__ nc, int32_t* __restrict__ ec, const DedupMap map, int32_t l2) {
+  const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x < LG_COUNTER_SLOTS) {
     int t = threadIdx.x;
@@ -145,7 +208,20 @@ __global__ void __launch_bounds__(kBlock) batch_generate_kernel(
   int32_t v = all_ids[pos % total_cap];
   ids[idx] = v;
   labels[idx] = all_labels[pos % total_cap];
-  if (v >= 0) red_min_u32(pm + v, (uint32_t)idx);  // position_map (:51): local index = first position
+  if (v >= 0) map_insert_min<HASHED>(map, (uint32_t)v, (uint32_t)idx, keep);  // position_map (:51): local index = first position
+}
+
+// HASHED only: batch-local id of every seed (= its first position; duplicates share it).  The hashed insert moves
+// resident words (a displaced key is in flight between two slots for a moment), so no kernel may look a vertex up
+// while another CTA of the same launch inserts: the hop-1 sample kernel reads these ids instead of the table, and
+// later hops read the previous hop's relabelled agg_src.
+__global__ void __launch_bounds__(kBlock) seed_local_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ nc,
+                                                            int32_t* __restrict__ seed_local, const DedupMap map, int32_t l2) {
+  const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc[1]) return;
+  const int32_t v = ids[i];
+  seed_local[i] = v >= 0 ? (int32_t)map_lookup<true>(map, (uint32_t)v, keep) : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -154,13 +230,14 @@ __global__ void __launch_bounds__(kBlock) batch_generate_kernel(
 struct SampleArgs {
   lg_topology topo;
   const int32_t* frontier_prev;  // hop > 1: global ids of the previous hop's sampled sources
+  const int32_t* seed_local;     // HASHED: batch-local ids of the seeds (seed_local_kernel)
   int32_t* gid_out;              // this hop's sampled sources (global ids), hop-relative positions
   int32_t* ids;
   int32_t* agg_src;
   int32_t* agg_dst;
   int32_t* nc;
   int32_t* ec;
-  uint32_t* pm;
+  DedupMap map;
   u64* tile_state;
   u64* anchors;
   HopState* hs;
@@ -170,10 +247,11 @@ struct SampleArgs {
   uint32_t fanout_magic;  // ceil(2^32 / fanout): slot / fanout as one multiply-high (slot < 2^16)
   int32_t relabel_prev;   // also write the previous hop's agg_src (its construct_graph) from the position map
   uint32_t batch_id, stream_id, k0, k1;
+  int32_t l2;  // lg_l2_hints()
   u64* trace;
 };
 
-template <int TILE_F, int RNG>
+template <int TILE_F, int RNG, bool HASHED>
 __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) {
   static_assert(TILE_F <= kBlock, "one thread per frontier entry of the tile");
   __shared__ long long s_start[TILE_F];
@@ -187,6 +265,7 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
 
   const int tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(&a.hs->sample_ticket, 1);
+  const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0), once = l2_policy((a.l2 & 8) ? 2 : 0);
   const bool first_hop = (a.hop == 1);
   const int32_t F = first_hop ? a.nc[1] : a.ec[1];          // :201-206
   const int32_t prev_edge_off = a.ec[0];
@@ -214,20 +293,24 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
       int32_t v = first_hop ? a.ids[i] : a.frontier_prev[i];
       if (v >= 0) {
         // batch-local index of the frontier vertex (position_map, :291-294): final since the previous op
-        fl = (int32_t)ld_ca_u32(a.pm + v);
-        if (a.relabel_prev) a.agg_src[prev_edge_off + i] = fl;  // construct_graph of the previous hop, fused
+        if (HASHED) {  // never from the table while this launch inserts (see seed_local_kernel)
+          fl = first_hop ? a.seed_local[i] : a.agg_src[prev_edge_off + i];
+        } else {
+          fl = (int32_t)map_lookup<false>(a.map, (uint32_t)v, keep);
+          if (a.relabel_prev) a.agg_src[prev_edge_off + i] = fl;  // construct_graph of the previous hop, fused
+        }
         int part = a.topo.n_parts;
         long long row = v;
         if (a.topo.directory) {
-          int32_t loc = a.topo.directory[v];
+          int32_t loc = ld_nc_s32_hint(a.topo.directory + v, keep);
           if (loc >= 0) {
             part = loc / a.topo.shard_rows;
             row = loc - part * a.topo.shard_rows;
           }
         }
         const int64_t* ip = a.topo.indptr[part];
-        start = ip[row];
-        deg = (int32_t)(ip[row + 1] - start);  // :226 (int32 col_size)
+        start = ld_nc_s64_hint(ip + row, keep);
+        deg = (int32_t)(ld_nc_s64_hint(ip + row + 1, keep) - start);  // :226 (int32 col_size)
         ind = a.topo.indices[part];
         cnt = deg < c ? deg : c;
         if (cnt < 0) cnt = 0;
@@ -267,18 +350,36 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
           const uint32_t slot = (uint32_t)(i0 + t) * (uint32_t)c + (uint32_t)j;
           const int32_t pick =
               pick_neighbor<RNG>(slot, s_deg[t], (uint32_t)a.hop, a.batch_id, a.stream_id, a.k0, a.k1);
-          w[u] = __ldg(s_indices[t] + s_start[t] + pick);  // :240-242
+          w[u] = ld_nc_s32_hint(s_indices[t] + s_start[t] + pick, once);  // :240-242
           p[u] = base + s_off[t] + j;
           fl[u] = s_flocal[t];
         }
       }
     }
+    if (HASHED) {  // all first probes of the group in flight together, then the (rare) continuations
+      u64 carry[kSlotUnroll], old[kSlotUnroll];
+      uint32_t sl[kSlotUnroll];
 #pragma unroll
-    for (int u = 0; u < kSlotUnroll; u++) {
-      if (p[u] >= 0) {
-        a.gid_out[p[u]] = w[u];
-        a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
-        red_min_u32(a.pm + w[u], kNewBit | (uint32_t)p[u]);
+      for (int u = 0; u < kSlotUnroll; u++) {
+        if (p[u] >= 0) {
+          a.gid_out[p[u]] = w[u];
+          a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
+          sl[u] = map_home(a.map, (uint32_t)w[u]);
+          carry[u] = map_pack((uint32_t)w[u], kNewBit | (uint32_t)p[u]);
+          old[u] = atom_min_u64_hint(a.map.table + sl[u], carry[u], keep);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSlotUnroll; u++)
+        if (p[u] >= 0) table_insert_finish(a.map, sl[u], carry[u], old[u], keep);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kSlotUnroll; u++) {
+        if (p[u] >= 0) {
+          a.gid_out[p[u]] = w[u];
+          a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
+          red_min_u32_hint(a.map.pm + w[u], kNewBit | (uint32_t)p[u], keep);
+        }
       }
     }
   }
@@ -297,23 +398,26 @@ struct RankArgs {
   int32_t* ids;
   int32_t* nc;
   int32_t* ec;
-  uint32_t* pm;
+  DedupMap map;
   u64* tile_state;
   u64* anchors;
   HopState* hs;
   int32_t hop;
+  int32_t publish;  // write the final local ids back into the map (needed by the next hop / the relabel pass)
   int32_t ids_cap;
+  int32_t l2;
   int32_t* status;
   u64* trace;
 };
 
-template <int ITEMS>
+template <int ITEMS, bool HASHED>
 __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
   static_assert(ITEMS % 4 == 0, "edges are loaded as int4");
   constexpr int TILE = kBlock * ITEMS;
   __shared__ int32_t s_red[kBlock / 32];
   __shared__ int32_t s_tile, s_last;
   const int tid = threadIdx.x;
+  const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0);
   if (tid == 0) s_tile = atomicAdd(&a.hs->rank_ticket, 1);
   const int32_t E = a.ec[2];
   const int32_t node_base = a.nc[0] + a.nc[1];  // :268
@@ -332,11 +436,22 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
       const int4 v = *reinterpret_cast<const int4*>(a.gid + p0 + k);
       w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
     }
+    // L1-cached: a line fetched before the owner publishes holds kNewBit|p_first, one fetched after holds the
+    // final id — neither can equal kNewBit|p for a non-owner, and an owner's word is only rewritten by itself
+    uint32_t sl[HASHED ? ITEMS : 1];
+    if (HASHED) {
+      u64 cur[ITEMS];
 #pragma unroll
-    for (int k = 0; k < ITEMS; k++) {
-      // L1-cached: a line fetched before the owner publishes holds kNewBit|p_first, one fetched after holds the
-      // final id — neither can equal kNewBit|p for a non-owner, and an owner's word is only rewritten by itself
-      q[k] = (p0 + k < E) ? ld_ca_u32(a.pm + w[k]) : 0u;
+      for (int k = 0; k < ITEMS; k++) {  // first probes in flight together
+        sl[k] = map_home(a.map, (uint32_t)w[k]);
+        cur[k] = (p0 + k < E) ? ld_ca_u64_hint(a.map.table + sl[k], keep) : 0ull;
+      }
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++)
+        q[k] = (p0 + k < E) ? table_find_finish(a.map, (uint32_t)w[k], &sl[k], cur[k], keep) : 0u;
+    } else {
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++) q[k] = (p0 + k < E) ? ld_ca_u32_hint(a.map.pm + w[k], keep) : 0u;
     }
     uint32_t mask = 0;
 #pragma unroll
@@ -355,7 +470,10 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
       if (mask & (1u << k)) {
         if (local < a.ids_cap) a.ids[local] = w[k];  // :270
         else *a.status = 1;
-        a.pm[w[k]] = (uint32_t)local;  // position_map :271
+        if (a.publish) {  // position_map :271
+          if (HASHED) st_u64_hint(a.map.table + sl[k], map_pack((uint32_t)w[k], (uint32_t)local), keep);
+          else st_u32_hint(a.map.pm + w[k], (uint32_t)local, keep);
+        }
         local++;
       }
     }
@@ -393,8 +511,10 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
 // construct_graph for the sources of the hop just ranked (:283-296): agg_src[e] = position_map[src].  Runs after the
 // rank kernel's counter_update: (ec[0], ec[1]) = (offset, count) of the hop's edges.  For every hop but the last
 // lg_run_batch folds this pass into the next hop's sample kernel (which reads the same words anyway).
+template <bool HASHED>
 __global__ void __launch_bounds__(kBlock) relabel_kernel(const int32_t* __restrict__ gid, int32_t* __restrict__ agg_src,
-                                                         const int32_t* __restrict__ ec, const uint32_t* pm) {
+                                                         const int32_t* __restrict__ ec, const DedupMap map, int32_t l2) {
+  const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   const int32_t off = ec[0], E = ec[1];
   const int32_t p0 = (blockIdx.x * kBlock + threadIdx.x) * 4;
   if (p0 >= E) return;
@@ -402,7 +522,7 @@ __global__ void __launch_bounds__(kBlock) relabel_kernel(const int32_t* __restri
   const int32_t w[4] = {v.x, v.y, v.z, v.w};
   uint32_t q[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) q[k] = (p0 + k < E) ? ld_ca_u32(pm + w[k]) : 0u;
+  for (int k = 0; k < 4; k++) q[k] = (p0 + k < E) ? map_lookup<HASHED>(map, (uint32_t)w[k], keep) : 0u;
 #pragma unroll
   for (int k = 0; k < 4; k++)
     if (p0 + k < E) agg_src[off + p0 + k] = (int32_t)q[k];
@@ -411,13 +531,14 @@ __global__ void __launch_bounds__(kBlock) relabel_kernel(const int32_t* __restri
 // ClearPosMap (:542-548): the position-map words of this batch's vertices go back to "not in the batch".
 // O(batch) work; the map itself is O(N) like the reference's, but never memset.
 __global__ void __launch_bounds__(kBlock) pm_clear_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ nc,
-                                                          uint32_t* pm) {
+                                                          uint32_t* pm, int32_t l2) {
+  const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   int32_t n = nc[LG_INTRABATCH_CON * 2 + 1];
   const int32_t seeds = nc[LG_INTRABATCH_CON * 3];
   if (seeds > n) n = seeds;  // before the first hop nc[7] is still 0
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int32_t v = ids[i];
-    if (v >= 0) pm[v] = kPmEmpty;
+    if (v >= 0) st_u32_hint(pm + v, kPmEmpty, keep);
   }
 }
 
@@ -489,9 +610,26 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
     LG_CUDA(cudaMalloc(&s->gid[b], (size_t)smax * sizeof(int32_t)));
     LG_CUDA(cudaMemset(s->gid[b], 0, (size_t)smax * sizeof(int32_t)));
   }
-  // position map: one word per vertex (the reference's position_map, engine/server.cu:224), 0xFFFFFFFF = absent
-  LG_CUDA(cudaMalloc(&s->pm, (size_t)num_nodes * sizeof(uint32_t)));
-  LG_CUDA(cudaMemset(s->pm, 0xFF, (size_t)num_nodes * sizeof(uint32_t)));
+  // position map.  DENSE: one word per vertex (the reference's position_map, engine/server.cu:224), 0xFFFFFFFF =
+  // absent; HASHED: 2^k >= 1.5 x num_ids packed words.  Dense while the map can stay L2-resident next to the
+  // gather's stream (LG_DENSE_MAX_MB, default 48 MB of the 126 MB L2); LG_DEDUP=dense|hash overrides.
+  {
+    int64_t dense_max_mb = 48;
+    if (const char* e = getenv("LG_DENSE_MAX_MB")) dense_max_mb = atoll(e);
+    s->hashed = (num_nodes * 4 > dense_max_mb * (1ll << 20)) ? 1 : 0;
+    if (const char* e = getenv("LG_DEDUP")) s->hashed = (e[0] == 'h' || e[0] == 'H') ? 1 : 0;
+  }
+  if (s->hashed) {
+    uint64_t slots = 1024;
+    while (slots < (uint64_t)s->num_ids * 3 / 2) slots <<= 1;
+    LG_REQUIRE(slots <= (1ull << 31), "lg_sampler_create: dedup table of %llu slots", (unsigned long long)slots);
+    s->table_mask = (uint32_t)(slots - 1);
+    LG_CUDA(cudaMalloc(&s->table, (size_t)slots * sizeof(u64)));
+    LG_CUDA(cudaMemset(s->table, 0xFF, (size_t)slots * sizeof(u64)));
+  } else {
+    LG_CUDA(cudaMalloc(&s->pm, (size_t)num_nodes * sizeof(uint32_t)));
+    LG_CUDA(cudaMemset(s->pm, 0xFF, (size_t)num_nodes * sizeof(uint32_t)));
+  }
   // small per-batch state
   int64_t bytes = sizeof(HopState) * LG_MAX_HOPS;
   bytes = (bytes + 255) & ~255ll;
@@ -524,6 +662,7 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   }
   LG_CUDA(cudaMalloc(&s->status, sizeof(int32_t)));
   LG_CUDA(cudaMemset(s->status, 0, sizeof(int32_t)));
+  if (s->hashed) LG_CUDA(cudaMalloc(&s->seed_local, (size_t)max_batch * sizeof(int32_t)));
   LG_CUDA(cudaMallocHost(&s->pinned_seeds, (size_t)max_batch * 2 * sizeof(int32_t)));
   LG_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   for (int h = 0; h <= LG_MAX_HOPS; h++) LG_CUDA(cudaEventCreateWithFlags(&s->ev_fork[h], cudaEventDisableTiming));
@@ -538,6 +677,8 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   if (!s) return 0;
   cudaSetDevice(s->device);
   cudaFree(s->pm);
+  cudaFree(s->table);
+  cudaFree(s->seed_local);
   cudaFree(s->gid[0]);
   cudaFree(s->gid[1]);
   cudaFree(s->small);
@@ -553,7 +694,10 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
 
 extern "C" int lg_sampler_reset(lg_sampler* s, lg_stream_t stream) {
   LG_REQUIRE(s, "null sampler");
-  LG_CUDA(cudaMemsetAsync(s->pm, 0xFF, (size_t)s->num_nodes * sizeof(uint32_t), (cudaStream_t)stream));
+  if (s->hashed)
+    LG_CUDA(cudaMemsetAsync(s->table, 0xFF, ((size_t)s->table_mask + 1) * sizeof(u64), (cudaStream_t)stream));
+  else
+    LG_CUDA(cudaMemsetAsync(s->pm, 0xFF, (size_t)s->num_nodes * sizeof(uint32_t), (cudaStream_t)stream));
   LG_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int32_t), (cudaStream_t)stream));
   s->pm_dirty = 0;
   return 0;
@@ -621,15 +765,25 @@ extern "C" int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* hos
 
 extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
   if (!s) return 0;
-  return s->num_nodes * 4 + 2 * s->slots_per_hop[s->n_hops] * 4 + s->small_bytes + 4;
+  const int64_t map_bytes = s->hashed ? ((int64_t)s->table_mask + 1) * 8 : s->num_nodes * 4;
+  return map_bytes + 2 * s->slots_per_hop[s->n_hops] * 4 + s->small_bytes + 4;
 }
 
 // the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
 static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
-  pm_clear_kernel<<<kSMs * 4, kBlock, 0, st>>>(b->ids, b->node_counter, s->pm);
-  LG_LAUNCH_OK();
+  if (!s->hashed) {  // HASHED: the table is re-initialised by the next lg_batch_generate instead
+    pm_clear_kernel<<<kSMs * 4, kBlock, 0, st>>>(b->ids, b->node_counter, s->pm, lg_l2_hints());
+    LG_LAUNCH_OK();
+  }
   s->pm_dirty = 0;
   return 0;
+}
+static DedupMap map_of(const lg_sampler* s) {
+  DedupMap m;
+  m.pm = s->pm;
+  m.table = s->table;
+  m.mask = s->table_mask;
+  return m;
 }
 
 extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32_t* all_ids,
@@ -645,6 +799,8 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
     int rc = clear_position_map(s, st, &s->dirty_batch);
     if (rc) return rc;
   }
+  if (s->hashed)  // O(batch)-sized table, L2-resident: one streaming memset instead of an O(batch) random clear
+    LG_CUDA(cudaMemsetAsync(s->table, 0xFF, ((size_t)s->table_mask + 1) * sizeof(u64), st));
   // reset of the per-batch scan state (tickets + tile aggregates); the position map needs no reset
   // (the reference memsets an N/8-byte bitmap here, :151)
   LG_CUDA(cudaMemsetAsync(s->small, 0, (size_t)s->small_bytes, st));
@@ -652,21 +808,26 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
   if (size < 0) size = 0;
   int grid = size > 0 ? (size + kBlock - 1) / kBlock : 1;
-  batch_generate_kernel<<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
-                                                 b->labels, b->node_counter, b->edge_counter, s->pm);
+  if (s->hashed) {
+    batch_generate_kernel<true><<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
+                                                         b->labels, b->node_counter, b->edge_counter, map_of(s), lg_l2_hints());
+    seed_local_kernel<<<grid, kBlock, 0, st>>>(b->ids, b->node_counter, s->seed_local, map_of(s), lg_l2_hints());
+  } else
+    batch_generate_kernel<false><<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
+                                                          b->labels, b->node_counter, b->edge_counter, map_of(s), lg_l2_hints());
   LG_LAUNCH_OK();
   s->pm_dirty = 1;
   s->dirty_batch = *b;
   return 0;
 }
 
-template <int RNG>
+template <int RNG, bool HASHED>
 static void launch_sample(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
   switch (tile_f) {
-    case 256: sample_hop_kernel<256, RNG><<<grid, kBlock, 0, st>>>(a); break;
-    case 128: sample_hop_kernel<128, RNG><<<grid, kBlock, 0, st>>>(a); break;
-    case 64: sample_hop_kernel<64, RNG><<<grid, kBlock, 0, st>>>(a); break;
-    default: sample_hop_kernel<32, RNG><<<grid, kBlock, 0, st>>>(a); break;
+    case 256: sample_hop_kernel<256, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    case 128: sample_hop_kernel<128, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    case 64: sample_hop_kernel<64, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    default: sample_hop_kernel<32, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
   }
 }
 
@@ -675,16 +836,21 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
                       uint64_t rng_seed, uint32_t batch_id, uint32_t stream_id, const lg_batch* b,
                       unsigned long long* edge_hotness, bool relabel_prev, bool relabel_own) {
   const int h = hop - 1;
+  if (s->hashed) {  // every hop relabels itself; the next hop reads agg_src instead of the table
+    relabel_prev = false;
+    relabel_own = true;
+  }
   SampleArgs a;
   a.topo = *topo;
   a.frontier_prev = s->gid[(h + 1) & 1];
+  a.seed_local = s->seed_local;
   a.gid_out = s->gid[h & 1];
   a.ids = b->ids;
   a.agg_src = b->agg_src;
   a.agg_dst = b->agg_dst;
   a.nc = b->node_counter;
   a.ec = b->edge_counter;
-  a.pm = s->pm;
+  a.map = map_of(s);
   a.tile_state = s->sample_state[h];
   a.anchors = s->sample_anchor[h];
   a.hs = s->hs + h;
@@ -697,33 +863,45 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   a.stream_id = stream_id;
   a.k0 = (uint32_t)rng_seed;
   a.k1 = (uint32_t)(rng_seed >> 32);
+  a.l2 = lg_l2_hints();
   a.trace = s->trace;
-  if (rng_kind == LG_RNG_MINSTD)
-    launch_sample<LG_RNG_MINSTD>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
-  else
-    launch_sample<LG_RNG_PHILOX>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+  if (rng_kind == LG_RNG_MINSTD) {
+    if (s->hashed) launch_sample<LG_RNG_MINSTD, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+    else launch_sample<LG_RNG_MINSTD, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+  } else {
+    if (s->hashed) launch_sample<LG_RNG_PHILOX, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+    else launch_sample<LG_RNG_PHILOX, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+  }
   LG_LAUNCH_OK();
   RankArgs r;
   r.gid = s->gid[h & 1];
   r.ids = b->ids;
   r.nc = b->node_counter;
   r.ec = b->edge_counter;
-  r.pm = s->pm;
+  r.map = map_of(s);
+  r.publish = 1;
   r.tile_state = s->rank_state[h];
   r.anchors = s->rank_anchor[h];
   r.hs = s->hs + h;
   r.hop = hop;
   r.ids_cap = b->num_ids;
+  r.l2 = lg_l2_hints();
   r.status = s->status;
   r.trace = s->trace;
-  if (s->rank_items[h] == 8)
-    rank_kernel<8><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
-  else
-    rank_kernel<4><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+  if (s->hashed) {
+    if (s->rank_items[h] == 8) rank_kernel<8, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+    else rank_kernel<4, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+  } else {
+    if (s->rank_items[h] == 8) rank_kernel<8, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+    else rank_kernel<4, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+  }
   LG_LAUNCH_OK();
   if (relabel_own) {
     const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
-    relabel_kernel<<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, s->pm);
+    if (s->hashed)
+      relabel_kernel<true><<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, map_of(s), lg_l2_hints());
+    else
+      relabel_kernel<false><<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, map_of(s), lg_l2_hints());
     LG_LAUNCH_OK();
   }
   return 0;

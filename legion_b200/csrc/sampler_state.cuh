@@ -20,6 +20,10 @@ struct lg_sampler {
   int64_t num_nodes;
   uint32_t* pm;          // position map [num_nodes]: 0xFFFFFFFF absent, kNewBit|edge position while a hop is open,
                          // else the batch-local id (engine/server.cu:224 position_map)
+  u64* table;            // HASHED layout of the same map: (vertex << 32 | value) words, open addressing
+  uint32_t table_mask;
+  int32_t* seed_local;   // HASHED: batch-local ids of the seeds [max_batch]
+  int32_t hashed;        // 0 dense pm, 1 hashed table (chosen at create time by the size of the graph)
   int32_t pm_dirty;      // a batch was generated and its words not yet released (lg_io_complete)
   lg_batch dirty_batch;
   int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)

@@ -8,6 +8,15 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["dense", "hash"])
+def dedup_layout(request, monkeypatch):
+    """every test runs with both layouts of the position map (csrc/sampler.cu: DENSE word per vertex / HASHED table)"""
+    monkeypatch.setenv("LG_DEDUP", request.param)
+    return request.param
+
+
 torch = pytest.importorskip("torch")
 
 from legion_b200 import capi, synth  # noqa: E402
