@@ -489,7 +489,7 @@ def run_ours(args):
                                 + (f", hottest {args.cache_ratio:.3f} of the rows in HBM ({cap} rows/GPU), the rest in pinned host memory (UVA)" if feat_host else ", fully HBM-cached")
                                 + (f"; topology in pinned host memory (UVA) with the hottest {args.topo_cache_ratio:.3f} of the adjacency lists cached in HBM ({topo_cap} rows/GPU)" if topo_host else "; topology replicated in HBM"),
                        "feature_cache_ratio": args.cache_ratio, "topology": args.topo, "topology_cache_ratio": args.topo_cache_ratio if topo_host else None,
-                       "rng": "philox4x32-10", "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
+                       "rng": "philox4x32-10", "position_map": ["dense u32[N]", "hashed L2-resident table"][dp.L.lg_sampler_dedup_layout(dp.sampler)], "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
                        "l2": "working set (topology + features + per-batch output, >1.5 GB) exceeds the 126 MB L2; every step samples different seeds"},
             "e2e": {"value": seeds / t_e2e, "unit": "seeds/s", "h2d_bytes_per_step": 2 * 4 * B, "d2h_bytes_per_step": 128,
                     "note": "every step: seed ids+labels copied from pinned host memory (H2D), lg_run_batch_host_async, both counter "
@@ -513,7 +513,10 @@ def run_ours(args):
             "clocks": clk,
         }
         # batch_generate + (sample, rank) per hop + the last hop's relabel + pm_clear + gathers (memsets/copies not counted)
-        out["gpu_launches"] = args.steps * (1 + 2 * H + 1 + 1 + n_gather_launches)
+        if dp.L.lg_sampler_dedup_layout(dp.sampler) == 1:  # hashed: + seed ids, a relabel per hop, no clear pass
+            out["gpu_launches"] = args.steps * (2 + 3 * H + n_gather_launches)
+        else:
+            out["gpu_launches"] = args.steps * (1 + 2 * H + 1 + 1 + n_gather_launches)
         tr = recorded_traffic()
         if tr:
             out["roofline"]["traffic"] = tr.get("traffic_bytes_per_step")

@@ -118,6 +118,10 @@ int lg_sampler_destroy(lg_sampler* s);
 /* full reset of the position map and the sticky status (after an overflow status or an aborted batch) */
 int lg_sampler_reset(lg_sampler* s, lg_stream_t stream);
 int64_t lg_sampler_scratch_bytes(const lg_sampler* s);
+/* layout of the position map chosen for this handle: 0 = dense (one 32-bit word per vertex, the reference's
+ * position_map), 1 = hashed (O(batch) L2-resident table; picked when 4*num_nodes bytes would not stay in L2).
+ * Environment: LG_DEDUP=dense|hash forces one, LG_DENSE_MAX_MB moves the threshold (default 48). */
+int32_t lg_sampler_dedup_layout(const lg_sampler* s);
 /* data mover used by lg_feature_cache_lookup: LG_GATHER_AUTO / LG_GATHER_LDG / LG_GATHER_TMA */
 int lg_sampler_set_gather_variant(lg_sampler* s, int32_t variant);
 /* how many gather launches lg_run_batch issues: 0 = one per lookup op (the reference's schedule);
@@ -224,6 +228,20 @@ int lg_run_batch_host_async(lg_sampler* s, lg_stream_t stream, const lg_topology
 int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache, const int32_t* ids,
                    int64_t n, float* dst, int32_t local_part, int32_t variant,
                    unsigned long long* tier_rows);
+
+/* ---- trainer-side block construction ----
+ * The reference trainer builds a DGL block from the COO of every layer on every step
+ * (training_backend/legion_graphsage.py:66-79, create_unitgraph_from_coo) and DGL then converts it to CSC for
+ * the SpMM.  lg_block_csc builds that CSC once from the CUDA-IPC buffers, on the trainer's stream:
+ * block h = edges [0, ec[9+h]) of agg_src/agg_dst, num_dst = nc[9+h-1], num_src = nc[9+h]
+ * (training_backend/ipc_cuda_kernel.cu:200-232).  indptr[num_dst+1]; indices[n_edges] = batch-local source of
+ * each in-edge; eids[n_edges] (may be NULL) = position of the edge in the COO.  In-edges of one destination keep
+ * their COO order (stable), so the result is a pure function of the COO.  Edges whose dst >= num_dst are invalid
+ * input.  workspace: lg_block_csc_workspace(max_edges) bytes of device memory. */
+int lg_block_csc_workspace(int64_t max_edges, int64_t* bytes);
+int lg_block_csc(lg_stream_t stream, const int32_t* agg_src, const int32_t* agg_dst, int64_t n_edges,
+                 int32_t num_dst, int32_t* indptr, int32_t* indices, int32_t* eids, void* workspace,
+                 int64_t workspace_bytes);
 
 /* ---- unified cache construction (cache/cache.cu:360-443,71-136,553-611) ---- */
 

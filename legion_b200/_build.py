@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "liblegion_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["runtime.cu", "sampler.cu", "gather.cu", "cache_build.cu", "synth.cu"]
+SOURCES = ["runtime.cu", "sampler.cu", "gather.cu", "cache_build.cu", "synth.cu", "blocks.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-ccbin", "/usr/bin/g++"]
 

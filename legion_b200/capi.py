@@ -50,6 +50,7 @@ _PROTOS = {
     "lg_sampler_destroy": (C.c_int, [vp]),
     "lg_sampler_reset": (C.c_int, [vp, vp]),
     "lg_sampler_scratch_bytes": (C.c_int64, [vp]),
+    "lg_sampler_dedup_layout": (C.c_int32, [vp]),
     "lg_sampler_set_gather_variant": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_overlap": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_gather_fusion": (C.c_int, [vp, C.c_int32]),
@@ -106,6 +107,8 @@ _PROTOS = {
     "lg_event_synchronize": (C.c_int, [vp]),
     "lg_stream_wait_event": (C.c_int, [vp, vp]),
     "lg_device_mem_info": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lg_block_csc_workspace": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),
+    "lg_block_csc": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int64]),
     # include/legion_b200_synth.h
     "lg_synth_indptr": (C.c_int, [vp, C.c_int64, C.c_double, C.c_int32, C.c_uint64, vp]),
     "lg_synth_indices": (C.c_int, [vp, C.c_int64, vp, C.c_uint64, vp]),

@@ -763,6 +763,8 @@ extern "C" int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* hos
   return 0;
 }
 
+extern "C" int32_t lg_sampler_dedup_layout(const lg_sampler* s) { return s ? s->hashed : -1; }
+
 extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
   if (!s) return 0;
   const int64_t map_bytes = s->hashed ? ((int64_t)s->table_mask + 1) * 8 : s->num_nodes * 4;

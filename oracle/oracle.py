@@ -69,6 +69,7 @@ def lib():
     L.lgo_dgl_sample.argtypes = [i64p, i32p, i32p, C.c_int32, i32p, C.c_int32, C.c_uint64, i32p, i32p, i32p,
                                  i32p, i64p, i64p, i64p, i32p]
     L.lgo_index_select.argtypes = [f32p, C.c_int32, i32p, C.c_int64, f32p]
+    L.lgo_block_csc.argtypes = [i32p, i32p, C.c_int64, C.c_int32, i32p, i32p, i32p]
     L.lgo_num_threads.restype = C.c_int32
     L.lgo_set_num_threads.argtypes = [C.c_int32]
     _lib = L
@@ -160,6 +161,15 @@ def feature_lookup(ids, node_off, cnt, directory, shards, cap, backing, dim, dst
     L.lgo_feature_lookup(np.ascontiguousarray(ids, np.int32), node_off, cnt, d, arr, cap,
                          backing.reshape(-1), N, dim, dst.reshape(-1))
     return dst
+
+
+def block_csc(src, dst, num_dst):
+    """COO -> CSC of one block, in-edges in COO order (lgo_block_csc)"""
+    src, dst = np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32)
+    e = len(src)
+    indptr, indices, eids = np.zeros(num_dst + 1, np.int32), np.zeros(max(e, 1), np.int32), np.zeros(max(e, 1), np.int32)
+    lib().lgo_block_csc(src if e else np.zeros(1, np.int32), dst if e else np.zeros(1, np.int32), e, num_dst, indptr, indices, eids)
+    return indptr, indices[:e], eids[:e]
 
 
 def hotness_rank(hot):
