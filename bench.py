@@ -527,6 +527,23 @@ def run_ours(args):
             np_ip, np_ix = ip.cpu().numpy(), ix.cpu().numpy()
         out["cpu_baseline"] = cpu_arm(shape, np_ip, np_ix, feat.cpu().numpy(), my_train, steps=args.cpu_steps,
                                       warmup=1)["cpu_baseline"]
+    # --- the drop-in boundary itself (rank 0, N=1): sampling_server binary -> shm/semaphores/CUDA IPC -> ipc_service ---
+    if rank == 0 and world == 1 and args.server_e2e and shape["name"] == "products" and not feat_host and not topo_host:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "server_e2e.py"), "--epochs", "10"],
+                               capture_output=True, text=True, timeout=600)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode == 0 and line:
+                j = json.loads(line[-1])
+                out["e2e_server"] = {"value": j["seeds_per_s"], "unit": "seeds/s", "ms_per_batch": j["ms_per_batch"],
+                                     "steps": j["train_steps_per_epoch"] * j["epochs"], "server_says": j["server_says"],
+                                     "note": "C++ sampling_server binary (dataset files, meta_config, presampling, cost model, cache fill) -> "
+                                             "simpleIPCshm + semaphores + CUDA-IPC buffers -> ipc_service.get_next/get_block_size/"
+                                             "synchronize consumer, wall clock over the training steps of 10 epochs"}
+            else:
+                out["e2e_server"] = {"unavailable": (r.stderr or r.stdout)[-300:]}
+        except Exception as ex:  # noqa: BLE001  (never lose the main line to the optional leg)
+            out["e2e_server"] = {"unavailable": repr(ex)[:300]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -625,6 +642,9 @@ def main():
                     help="0 one stream; 1 gathers overlap the next hop; 2 pipelined across the two batch slots")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--server-e2e", action="store_true",
+                    help="also run scripts/server_e2e.py (the sampling_server binary feeding an ipc_service consumer) and "
+                         "report it as e2e_server")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 50 and "--steps" not in sys.argv:

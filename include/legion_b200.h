@@ -288,6 +288,15 @@ int lg_cost_model(const unsigned long long* sorted_node_hotness,
                   const int64_t* indptr, int64_t num_nodes, int32_t dim, int64_t cache_bytes,
                   int32_t kg, uint64_t topo_trans, uint64_t feat_trans, int32_t* node_capacity,
                   int32_t* edge_capacity, double* alpha);
+/* Same sweep with the saturation the reference lacks: a split whose feature (or topology) share already holds EVERY
+ * vertex still counts its transactions and capacity (the reference skips the update when node_num == total,
+ * cache/cache.cu:528-535, so a cache larger than the dataset — the normal case with 180 GB of HBM — ends with both
+ * capacities 0), and node_num_feat is clamped to num_nodes.  Used by sampling_server (DESIGN.md deviation 8). */
+int lg_cost_model_saturating(const unsigned long long* sorted_node_hotness,
+                  const unsigned long long* sorted_edge_hotness, const int32_t* topo_order,
+                  const int64_t* indptr, int64_t num_nodes, int32_t dim, int64_t cache_bytes,
+                  int32_t kg, uint64_t topo_trans, uint64_t feat_trans, int32_t* node_capacity,
+                  int32_t* edge_capacity, double* alpha);
 
 /* ---- device plumbing a non-CUDA host needs (storage/storage_management.cu:5-23,100-115;
  *      engine/ipc_service.cu:163-169; training_backend/ipc_cuda_kernel.cu:62-68) ---- */

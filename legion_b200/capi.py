@@ -83,6 +83,8 @@ _PROTOS = {
     "lg_fill_i32": (C.c_int, [vp, vp, C.c_int32, C.c_int64]),
     "lg_cost_model": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    "lg_cost_model_saturating": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
+                                C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "lg_device_count": (C.c_int, [C.POINTER(C.c_int32)]),
     "lg_set_device": (C.c_int, [C.c_int32]),
     "lg_enable_peer_access": (C.c_int, [C.c_int32]),

@@ -202,11 +202,11 @@ extern "C" int lg_topo_shard_fill(lg_stream_t stream, const int32_t* order, int3
 
 // CostModel — host arithmetic of cache/cache.cu:445-551 (float accumulators, 1 % alpha sweep,
 // first maximum, +1 on both capacities).  Not a copy of the oracle: same published algorithm.
-extern "C" int lg_cost_model(const unsigned long long* sorted_node_hotness,
-                             const unsigned long long* sorted_edge_hotness, const int32_t* topo_order,
-                             const int64_t* indptr, int64_t num_nodes, int32_t dim, int64_t cache_bytes, int32_t kg,
-                             uint64_t topo_trans, uint64_t feat_trans, int32_t* node_capacity, int32_t* edge_capacity,
-                             double* alpha) {
+static int cost_model_impl(const unsigned long long* sorted_node_hotness,
+                           const unsigned long long* sorted_edge_hotness, const int32_t* topo_order,
+                           const int64_t* indptr, int64_t num_nodes, int32_t dim, int64_t cache_bytes, int32_t kg,
+                           uint64_t topo_trans, uint64_t feat_trans, int32_t* node_capacity, int32_t* edge_capacity,
+                           double* alpha, bool saturate) {
   LG_REQUIRE(sorted_node_hotness && sorted_edge_hotness && topo_order && indptr && node_capacity && edge_capacity,
              "lg_cost_model: null argument");
   LG_REQUIRE(num_nodes > 0 && dim > 0 && cache_bytes > 0 && kg > 0, "lg_cost_model: bad size");
@@ -231,19 +231,20 @@ extern "C" int lg_cost_model(const unsigned long long* sorted_node_hotness,
   const int64_t row_bytes = (int64_t)dim * (int64_t)sizeof(float);
   int64_t k = 0;
   for (int64_t mem = 0; mem < total_mem; mem += step, k++) {
-    int32_t n_feat = ((uint64_t)mem > (uint64_t)n * (uint64_t)row_bytes) ? (int32_t)n
-                                                                          : (int32_t)((k + 1) * (step / row_bytes));
+    int64_t n_feat64 = ((uint64_t)mem > (uint64_t)n * (uint64_t)row_bytes) ? n : (k + 1) * (step / row_bytes);
+    if (saturate && n_feat64 > n) n_feat64 = n;
+    const int32_t n_feat = (int32_t)n_feat64;
     int32_t n_topo;
     if ((uint64_t)mem > mem_prefix[n - 1])
       n_topo = (int32_t)n;
     else
       n_topo = (int32_t)(std::lower_bound(mem_prefix.begin(), mem_prefix.end(), (uint64_t)mem) - mem_prefix.begin());
-    if (n_topo < n) {
+    if (n_topo < n || saturate) {
       const uint64_t pre = n_topo > 0 ? edge_prefix[n_topo - 1] : 0;
       t_topo[k] = (float)(topo_trans * 1.0 / (double)edge_prefix[n - 1] * (double)pre);
       c_topo[k] = (float)(n_topo / kg);
     }
-    if (n_feat < n) {
+    if (n_feat < n || saturate) {
       const uint64_t pre = n_feat > 0 ? node_prefix[n_feat - 1] : 0;
       t_feat[k] = (float)(feat_trans * 1.0 / (double)node_prefix[n - 1] * (double)pre);
       c_feat[k] = (float)(n_feat / kg);
@@ -255,4 +256,22 @@ extern "C" int lg_cost_model(const unsigned long long* sorted_node_hotness,
   *node_capacity = (int32_t)(c_feat[steps - 1 - best] + 1);
   *edge_capacity = (int32_t)(c_topo[best] + 1);
   return 0;
+}
+
+extern "C" int lg_cost_model(const unsigned long long* sorted_node_hotness,
+                             const unsigned long long* sorted_edge_hotness, const int32_t* topo_order,
+                             const int64_t* indptr, int64_t num_nodes, int32_t dim, int64_t cache_bytes, int32_t kg,
+                             uint64_t topo_trans, uint64_t feat_trans, int32_t* node_capacity, int32_t* edge_capacity,
+                             double* alpha) {
+  return cost_model_impl(sorted_node_hotness, sorted_edge_hotness, topo_order, indptr, num_nodes, dim, cache_bytes, kg,
+                         topo_trans, feat_trans, node_capacity, edge_capacity, alpha, false);
+}
+
+extern "C" int lg_cost_model_saturating(const unsigned long long* sorted_node_hotness,
+                                        const unsigned long long* sorted_edge_hotness, const int32_t* topo_order,
+                                        const int64_t* indptr, int64_t num_nodes, int32_t dim, int64_t cache_bytes,
+                                        int32_t kg, uint64_t topo_trans, uint64_t feat_trans, int32_t* node_capacity,
+                                        int32_t* edge_capacity, double* alpha) {
+  return cost_model_impl(sorted_node_hotness, sorted_edge_hotness, topo_order, indptr, num_nodes, dim, cache_bytes, kg,
+                         topo_trans, feat_trans, node_capacity, edge_capacity, alpha, true);
 }

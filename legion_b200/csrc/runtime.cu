@@ -5,6 +5,9 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <sys/mman.h>
+#include <mutex>
+#include <vector>
 #include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
@@ -69,13 +72,58 @@ extern "C" int lg_device_free(void* ptr) {
   LG_CUDA(cudaFree(ptr));
   return 0;
 }
+// Pinned, device-mapped host memory (storage/storage_management.cu:108-109 uses cudaHostAllocMapped).
+// LG_HOST_HUGEPAGES=1: large regions come from an anonymous mapping advised to transparent huge pages and are then
+// registered (cudaHostRegisterMapped) — fewer host page-table / IOMMU entries behind the random UVA reads of the
+// host tiers.  Registered regions are remembered so lg_host_free can undo the right way.
+namespace {
+struct HugeRegion {
+  void* p;
+  size_t bytes;
+};
+std::mutex g_huge_mu;
+std::vector<HugeRegion> g_huge;
+}  // namespace
 extern "C" int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t bytes) {
   LG_REQUIRE(host_ptr && bytes >= 0, "lg_host_alloc_mapped: bad argument");
-  LG_CUDA(cudaHostAlloc(host_ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocMapped | cudaHostAllocPortable));
+  static const bool huge = [] {
+    const char* e = getenv("LG_HOST_HUGEPAGES");
+    return e && atoi(e) != 0;
+  }();
+  if (huge && bytes >= (64ll << 20)) {
+    const size_t two_mb = 2u << 20;
+    const size_t len = ((size_t)bytes + two_mb - 1) / two_mb * two_mb;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    LG_REQUIRE(p != MAP_FAILED, "lg_host_alloc_mapped: mmap of %zu bytes failed", len);
+    madvise(p, len, MADV_HUGEPAGE);
+    for (size_t off = 0; off < len; off += two_mb) ((volatile char*)p)[off] = 0;  // fault the huge pages in
+    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+      munmap(p, len);
+      return lg_set_error("cudaHostRegister(%zu bytes) -> %s", len, cudaGetErrorString(e));
+    }
+    *host_ptr = p;
+    {
+      std::lock_guard<std::mutex> g(g_huge_mu);
+      g_huge.push_back({p, len});
+    }
+  } else {
+    LG_CUDA(cudaHostAlloc(host_ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocMapped | cudaHostAllocPortable));
+  }
   if (device_ptr) LG_CUDA(cudaHostGetDevicePointer(device_ptr, *host_ptr, 0));
   return 0;
 }
 extern "C" int lg_host_free(void* host_ptr) {
+  {
+    std::lock_guard<std::mutex> g(g_huge_mu);
+    for (size_t i = 0; i < g_huge.size(); i++)
+      if (g_huge[i].p == host_ptr) {
+        cudaHostUnregister(host_ptr);
+        munmap(host_ptr, g_huge[i].bytes);
+        g_huge.erase(g_huge.begin() + i);
+        return 0;
+      }
+  }
   LG_CUDA(cudaFreeHost(host_ptr));
   return 0;
 }

@@ -62,6 +62,7 @@ def lib():
     L.lgo_cost_model.argtypes = [u64p, u64p, i32p, i64p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                  C.c_uint64, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_double)]
+    L.lgo_cost_model_saturating.argtypes = L.lgo_cost_model.argtypes
     L.lgo_coordinate.argtypes = [i32p, i32p, i32p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p,
                                  C.POINTER(C.c_int32)]
     L.lgo_mode_of.argtypes = [C.c_int32, i32p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -210,10 +211,12 @@ def fill_topo_shard(order, cap, kg, j, indptr, indices):
     return sip, sidx[: int(sip[-1])]
 
 
-def cost_model(sorted_node_hot, sorted_edge_hot, topo_order, indptr, dim, cache_bytes, kg, topo_trans, feat_trans):
+def cost_model(sorted_node_hot, sorted_edge_hot, topo_order, indptr, dim, cache_bytes, kg, topo_trans, feat_trans,
+               saturating=False):
     nc_, ec_, al = C.c_int32(), C.c_int32(), C.c_double()
     n = len(topo_order)
-    lib().lgo_cost_model(np.ascontiguousarray(sorted_node_hot, np.uint64),
+    fn = lib().lgo_cost_model_saturating if saturating else lib().lgo_cost_model
+    fn(np.ascontiguousarray(sorted_node_hot, np.uint64),
                          np.ascontiguousarray(sorted_edge_hot, np.uint64),
                          np.ascontiguousarray(topo_order, np.int32), np.ascontiguousarray(indptr, np.int64),
                          n, dim, cache_bytes, kg, topo_trans, feat_trans, C.byref(nc_), C.byref(ec_), C.byref(al))

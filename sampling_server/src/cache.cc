@@ -3,6 +3,7 @@
 // directories instead of bcht maps, one descriptor struct per GPU instead of device pointer tables.
 #include "cache.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 
@@ -88,10 +89,20 @@ void UnifiedCache::CostModel(int, FeatureStorage* feature, GraphStorage* graph, 
     LGCHECK(lg_memcpy_d2h(at.data(), AT_[i], n * 8, nullptr));
     LGCHECK(lg_memcpy_d2h(qt.data(), QT_[i], n * 4, nullptr));
     LGCHECK(lg_stream_synchronize(nullptr));
+    // The reference feeds Intel-PCM PCIe counters here and they are disabled ({0,0}, server.cu:106), which removes the
+    // topology term altogether.  Their stand-in: the presampling epoch issued one PCIe read transaction per sampled
+    // neighbour (a 4-byte read still costs a whole transaction) = the sum of the edge hotness counters.
+    if (topo_trans == 0)
+      for (int64_t v = 0; v < n; v++) topo_trans += at[v];
     int32_t ncap = 0, ecap = 0;
     double alpha = 0;
-    LGCHECK(lg_cost_model(af.data(), at.data(), qt.data(), graph->HostIndptr(), n, float_feature_len_, cache_memory_, Kg_,
-                          topo_trans, feat_trans, &ncap, &ecap, &alpha));
+    const char* cm = std::getenv("LEGION_COSTMODEL");
+    if (cm && std::strcmp(cm, "reference") == 0)  // the reference's rule verbatim: capacity 0 once everything fits
+      LGCHECK(lg_cost_model(af.data(), at.data(), qt.data(), graph->HostIndptr(), n, float_feature_len_, cache_memory_, Kg_,
+                            counters[0] + counters[1], feat_trans, &ncap, &ecap, &alpha));
+    else
+      LGCHECK(lg_cost_model_saturating(af.data(), at.data(), qt.data(), graph->HostIndptr(), n, float_feature_len_,
+                                       cache_memory_, Kg_, topo_trans, feat_trans, &ncap, &ecap, &alpha));
     std::cout << "Alpha: " << alpha << " on Clique: " << i << std::endl;
     std::cout << "Feat capacity: " << ncap - 1 << " Topo capacity: " << ecap - 1 << " on Clique: " << i << std::endl;
     node_capacity_.push_back(ncap);

@@ -77,3 +77,16 @@ def test_cost_model_matches_oracle(oracle):
                              kg, tt, ft, ctypes.byref(a), ctypes.byref(b), ctypes.byref(al))
         assert rc == 0
         assert (a.value, b.value, al.value) == want
+    # the saturating variant (DESIGN.md deviation 8): same sweep, but a cache larger than the dataset caches the dataset
+    for cache_bytes, kg, tt, ft in [(200_000, 1, 0, 10 ** 6), (50_000, 4, 10 ** 5, 10 ** 6), (10 ** 9, 1, 10 ** 6, 10 ** 6),
+                                    (10 ** 9, 4, 10 ** 6, 10 ** 6), (10 ** 11, 8, 0, 10 ** 6)]:
+        want = oracle.cost_model(nh, eh, order, indptr, 16, cache_bytes, kg, tt, ft, saturating=True)
+        a, b, al = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_double()
+        rc = L.lg_cost_model_saturating(nh.ctypes.data, eh.ctypes.data, order.ctypes.data, indptr.ctypes.data, N, 16,
+                                        cache_bytes, kg, tt, ft, ctypes.byref(a), ctypes.byref(b), ctypes.byref(al))
+        assert rc == 0
+        assert (a.value, b.value, al.value) == want
+        if cache_bytes >= 10 ** 9:  # everything fits: every vertex is cached (+1 as in the reference, cache.cu:547-548)
+            assert a.value == N // kg + 1 and b.value == N // kg + 1, (a.value, b.value)
+    ref = oracle.cost_model(nh, eh, order, indptr, 16, 10 ** 9, 1, 10 ** 6, 10 ** 6)
+    assert ref[0] == 1 and ref[1] == 1  # the reference's own rule ends with capacity 0 (+1) when everything fits
