@@ -642,9 +642,9 @@ def main():
                     help="0 one stream; 1 gathers overlap the next hop; 2 pipelined across the two batch slots")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--server-e2e", action="store_true",
-                    help="also run scripts/server_e2e.py (the sampling_server binary feeding an ipc_service consumer) and "
-                         "report it as e2e_server")
+    ap.add_argument("--no-server-e2e", dest="server_e2e", action="store_false",
+                    help="skip the e2e_server leg (scripts/server_e2e.py: the sampling_server binary feeding an ipc_service "
+                         "consumer over shm/semaphores/CUDA IPC; N=1, products workload only, ~30 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 50 and "--steps" not in sys.argv:

@@ -11,9 +11,9 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out
 free -g > gpurun_out/host_mem.txt; nproc >> gpurun_out/host_mem.txt
 echo "== pytest gpu"; timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_gpu_m.log
 timeout 600 python bench.py > gpurun_out/bench_m_default.json 2> gpurun_out/bench_m.err; show gpurun_out/bench_m_default.json "products default"
-for nf in 1 3 4; do timeout 600 python bench.py --no-cpu-baseline --inflight $nf > gpurun_out/bench_m_if$nf.json 2> gpurun_out/bench_m.err; show gpurun_out/bench_m_if$nf.json "products inflight$nf"; done
-timeout 600 python bench.py --no-cpu-baseline --inflight 1 --overlap 1 > gpurun_out/bench_m_ov1.json 2> gpurun_out/bench_m.err; show gpurun_out/bench_m_ov1.json "products inflight1 overlap1"
-timeout 600 python bench.py --no-cpu-baseline --inflight 1 --overlap 0 > gpurun_out/bench_m_ov0.json 2> gpurun_out/bench_m.err; show gpurun_out/bench_m_ov0.json "products inflight1 overlap0"
+for nf in 1 3 4; do timeout 600 python bench.py --no-cpu-baseline --no-server-e2e --inflight $nf > gpurun_out/bench_m_if$nf.json 2> gpurun_out/bench_m.err; show gpurun_out/bench_m_if$nf.json "products inflight$nf"; done
+timeout 600 python bench.py --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 1 > gpurun_out/bench_m_ov1.json 2> gpurun_out/bench_m.err; show gpurun_out/bench_m_ov1.json "products inflight1 overlap1"
+timeout 600 python bench.py --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/bench_m_ov0.json 2> gpurun_out/bench_m.err; show gpurun_out/bench_m_ov0.json "products inflight1 overlap0"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sample_hop|rank_relabel" -s 16 -c 4 -o gpurun_out/prof_sampler_m -f \
-  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --inflight 1 --overlap 0 > gpurun_out/ncu_m.log 2>&1
+  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/ncu_m.log 2>&1
 ls -la gpurun_out

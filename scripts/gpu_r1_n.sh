@@ -13,10 +13,10 @@ echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | ta
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke_n.log
 timeout 600 python bench.py > gpurun_out/bench_n_default.json 2> gpurun_out/bench_n.err; show gpurun_out/bench_n_default.json "products default"
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_n_reference.json 2>> gpurun_out/bench_n.err; tail -c 600 gpurun_out/bench_n_reference.json
-timeout 600 python bench.py --no-cpu-baseline --inflight 1 --overlap 0 > gpurun_out/bench_n_ov0.json 2>> gpurun_out/bench_n.err; show gpurun_out/bench_n_ov0.json "products inflight1 overlap0"
+timeout 600 python bench.py --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/bench_n_ov0.json 2>> gpurun_out/bench_n.err; show gpurun_out/bench_n_ov0.json "products inflight1 overlap0"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_n.csv \
-  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --inflight 1 --overlap 0 > gpurun_out/ncu_launch_n.log 2>&1
+  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/ncu_launch_n.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gather_|sample_hop|rank_kernel|relabel_kernel|batch_generate|pm_clear" -s 36 -c 8 -o gpurun_out/prof_all_n -f \
-  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --inflight 1 --overlap 0 > gpurun_out/ncu_full_n.log 2>&1
+  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/ncu_full_n.log 2>&1
 ncu -i gpurun_out/prof_all_n.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__waves_per_multiprocessor,lts__t_sector_hit_rate.pct,smsp__inst_executed.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum > gpurun_out/prof_all_n_raw.csv 2>&1
 ls -la gpurun_out

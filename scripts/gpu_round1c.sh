@@ -4,8 +4,8 @@ mkdir -p gpurun_out
 echo "== pytest gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 | tee gpurun_out/pytest_gpu3.log
 echo "== sweep v2"; timeout 1500 python scripts/gather_sweep.py 2>&1 | tee gpurun_out/gather_sweep_v2.txt
 for ov in 2 1 0; do
-echo "== bench overlap $ov"; timeout 600 python bench.py --no-cpu-baseline --overlap $ov > gpurun_out/bench_ov$ov.json 2> gpurun_out/bench_ov$ov.err; python -c "
+echo "== bench overlap $ov"; timeout 600 python bench.py --no-cpu-baseline --no-server-e2e --overlap $ov > gpurun_out/bench_ov$ov.json 2> gpurun_out/bench_ov$ov.err; python -c "
 import json;j=json.load(open('gpurun_out/bench_ov$ov.json'));print(j['value'],j['ms_per_step'],j['e2e']['value'],j['roofline']['frac'],j['breakdown_ms'])"; tail -2 gpurun_out/bench_ov$ov.err
 done
-echo "== bench tma pipelined"; timeout 600 python bench.py --no-cpu-baseline --gather tma > gpurun_out/bench_tma2.json 2> gpurun_out/bench_tma2.err; python -c "
+echo "== bench tma pipelined"; timeout 600 python bench.py --no-cpu-baseline --no-server-e2e --gather tma > gpurun_out/bench_tma2.json 2> gpurun_out/bench_tma2.err; python -c "
 import json;j=json.load(open('gpurun_out/bench_tma2.json'));print(j['value'],j['ms_per_step'],j['e2e']['value'],j['roofline']['frac'],j['breakdown_ms'])"

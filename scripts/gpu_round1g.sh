@@ -9,7 +9,7 @@ j=json.loads(line);print('$2', round(j['value']/1e6,2),'M seeds/s', round(j['ms_
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
 echo "== pytest gpu"; timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_gpu7.log
 for w in 1 8; do
-LG_LOOKBACK_WIDE=$w timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_g_n1_w$w.json 2> gpurun_out/bench_g.err; show gpurun_out/bench_g_n1_w$w.json "N1 wide=$w"; tail -2 gpurun_out/bench_g.err
+LG_LOOKBACK_WIDE=$w timeout 600 python bench.py --no-cpu-baseline --no-server-e2e > gpurun_out/bench_g_n1_w$w.json 2> gpurun_out/bench_g.err; show gpurun_out/bench_g_n1_w$w.json "N1 wide=$w"; tail -2 gpurun_out/bench_g.err
 done
 timeout 900 $TR bench.py --gpus 2 --no-cpu-baseline > gpurun_out/bench_g_n2_kg1.json 2> gpurun_out/bench_g.err; show gpurun_out/bench_g_n2_kg1.json "N2 kg=auto"; grep -v "^\*\|OMP" gpurun_out/bench_g.err | tail -2
 timeout 900 $TR bench.py --gpus 2 --no-cpu-baseline --kg 2 > gpurun_out/bench_g_n2_kg2.json 2> gpurun_out/bench_g.err; show gpurun_out/bench_g_n2_kg2.json "N2 kg=2 tma3"

@@ -13,8 +13,8 @@ echo "== bench ukunion"; timeout 1200 python bench.py --workload ukunion --steps
 nvidia-smi --query-gpu=memory.used --format=csv
 echo "== ncu launches (serial schedule)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_final.csv \
-  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --inflight 1 --overlap 0 > gpurun_out/ncu_l2.log 2>&1
+  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/ncu_l2.log 2>&1
 echo "== ncu full (gather_tma, sample_hop, rank_relabel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gather_tma|sample_hop|rank_relabel" -s 25 -c 10 -o gpurun_out/prof_final -f \
-  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --inflight 1 --overlap 0 > gpurun_out/ncu_f4.log 2>&1
+  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/ncu_f4.log 2>&1
 ls -la gpurun_out | tail -8

@@ -89,3 +89,44 @@ def test_server_to_trainer_handoff(oracle, tmp_path, fanout, cache_bytes):
     finally:
         if proc.poll() is None:
             proc.kill()
+
+
+@pytest.mark.parametrize("gpus,agg_mode,cache_bytes", [(2, "1.0", 150_000), (2, "0.0", 10_000_000)])
+def test_server_multi_gpu_handoff(oracle, tmp_path, gpus, agg_mode, cache_bytes):
+    """one server process, one thread per GPU (engine/server.cu:122-130), partitioned (Kg=2) or replicated (Kg=1) cache
+    read over cudaDeviceEnablePeerAccess; one trainer process per GPU (rank == device) checks every batch"""
+    from legion_b200 import dataset, synth
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs >= {gpus} GPUs")
+    N, D, B, epochs, seed, fanout = 8000, 16, 200, 2, 4242, [10, 5]
+    indptr, indices = synth.graph(N, 5.0, 300, 22)
+    feat = synth.features(0, N, D, 22)
+    labels = synth.labels(N, 7)
+    train, valid, test = synth.split_sets(N, 22, train_frac=0.25, valid=900, test=700)
+    data = str(tmp_path / "data") + "/"
+    dataset.write_dataset(data, indptr, indices, feat, labels, train, valid, test)
+    cwd = str(tmp_path)
+    dataset.write_meta_config(cwd, data, B, N, len(indices), D, len(train), len(valid), len(test), cache_bytes, epochs, fanout=fanout)
+    for f in os.listdir("/dev/shm"):
+        if f.startswith("sem.sem_") or f == "simpleIPCshm":
+            os.unlink(os.path.join("/dev/shm", f))
+    proc = subprocess.Popen([BIN, str(gpus), agg_mode], cwd=cwd, env=dict(os.environ, LEGION_SEED=str(seed)), stdout=subprocess.PIPE,
+                            stderr=subprocess.STDOUT, text=True)
+    consumers = []
+    try:
+        _wait_ready(proc)
+        for g in range(gpus):
+            cmd = [sys.executable, os.path.join(ROOT, "tests", "server_consumer.py"), str(g), str(gpus), data, str(N), str(len(indices)),
+                   str(D), str(B), str(epochs), str(seed)] + [str(f) for f in fanout]
+            consumers.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        for g, c in enumerate(consumers):
+            out, _ = c.communicate(timeout=300)
+            assert c.returncode == 0 and f"consumer {g} ok" in out, out[-3000:]
+        tail, _ = proc.communicate(timeout=60)
+        assert "Server Stopped" in tail and proc.returncode == 0, tail[-2000:]
+    finally:
+        for c in consumers:
+            if c.poll() is None:
+                c.kill()
+        if proc.poll() is None:
+            proc.kill()
