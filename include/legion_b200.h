@@ -305,6 +305,16 @@ int lg_set_device(int32_t device);
 int lg_enable_peer_access(int32_t n_devices);
 int lg_device_alloc(void** ptr, int64_t bytes); /* plain cudaMalloc: legacy-IPC exportable */
 int lg_device_free(void* ptr);
+/* Device memory that OTHER PROCESSES map at full page size (cache shards of the one-process-per-GPU deployment):
+ * cuMemCreate + POSIX-fd export / cuMemImportFromShareableHandle + cuMemMap.  A legacy cudaIpcOpenMemHandle mapping
+ * is read through small pages by the importer and random row reads out of a multi-GB peer shard collapse
+ * (profiles/r01b_peer_mapping.md); the trainer-facing batch buffers stay legacy-IPC (engine/ipc_service.cu:163-169).
+ * lg_vmm_alloc allocates on the current device and returns a file descriptor to pass to the peers (SCM_RIGHTS);
+ * lg_vmm_import maps a received descriptor for the current device; both sizes are rounded up to 2 MB. */
+int64_t lg_vmm_round_up(int64_t bytes);
+int lg_vmm_alloc(int64_t bytes, void** ptr, int32_t* shareable_fd);
+int lg_vmm_import(int32_t shareable_fd, int64_t bytes, void** ptr);
+int lg_vmm_free(void* ptr);
 int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t bytes); /* cudaHostAllocMapped */
 int lg_host_free(void* host_ptr);
 int lg_ipc_export(const void* device_ptr, unsigned char handle[64]);

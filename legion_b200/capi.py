@@ -90,6 +90,10 @@ _PROTOS = {
     "lg_enable_peer_access": (C.c_int, [C.c_int32]),
     "lg_device_alloc": (C.c_int, [C.POINTER(vp), C.c_int64]),
     "lg_device_free": (C.c_int, [vp]),
+    "lg_vmm_round_up": (C.c_int64, [C.c_int64]),
+    "lg_vmm_alloc": (C.c_int, [C.c_int64, C.POINTER(vp), C.POINTER(C.c_int32)]),
+    "lg_vmm_import": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(vp)]),
+    "lg_vmm_free": (C.c_int, [vp]),
     "lg_host_alloc_mapped": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_int64]),
     "lg_host_free": (C.c_int, [vp]),
     "lg_ipc_export": (C.c_int, [vp, C.c_char * 64]),

@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include <sys/mman.h>
+#include <unistd.h>
 #include <mutex>
 #include <vector>
 #include <stdlib.h>
@@ -63,6 +64,174 @@ extern "C" int lg_enable_peer_access(int32_t n_devices) {
   LG_CUDA(cudaSetDevice(cur));
   return 0;
 }
+// ---- VMM allocations for cache shards that other processes map (one process per GPU) ----
+// A legacy cudaIpcOpenMemHandle mapping is read through small pages on the importing GPU: random 512-byte rows out of
+// a 2.8 GB peer shard reach 95 GB/s, out of a 0.5 GB shard 630 GB/s (profiles/r01b_peer_mapping.md).  cuMemCreate +
+// cuMemExportToShareableHandle (POSIX fd) + cuMemMap on the importer keeps the allocation's 2 MB pages.  The driver
+// entry points are fetched through cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda
+// (it must still load on a box without a GPU).
+#include <cuda.h>
+namespace {
+struct Vmm {
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle);
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t);
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+  CUresult (*MemUnmap)(CUdeviceptr, size_t);
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+  CUresult (*MemExport)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+  CUresult (*MemImport)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
+  CUresult (*MemGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+  bool ok = false;
+};
+int vmm_load(Vmm* v) {
+  static Vmm cached;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaFree(0);  // make sure the primary context exists
+    struct {
+      const char* name;
+      void** fn;
+    } tab[] = {{"cuMemCreate", (void**)&cached.MemCreate},
+               {"cuMemRelease", (void**)&cached.MemRelease},
+               {"cuMemAddressReserve", (void**)&cached.MemAddressReserve},
+               {"cuMemAddressFree", (void**)&cached.MemAddressFree},
+               {"cuMemMap", (void**)&cached.MemMap},
+               {"cuMemUnmap", (void**)&cached.MemUnmap},
+               {"cuMemSetAccess", (void**)&cached.MemSetAccess},
+               {"cuMemExportToShareableHandle", (void**)&cached.MemExport},
+               {"cuMemImportFromShareableHandle", (void**)&cached.MemImport},
+               {"cuMemGetAllocationGranularity", (void**)&cached.MemGranularity}};
+    bool all = true;
+    for (auto& t : tab) {
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(t.name, t.fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*t.fn)
+        all = false;
+    }
+    cudaGetLastError();
+    cached.ok = all;
+  }
+  *v = cached;
+  return cached.ok ? 0 : lg_set_error("CUDA VMM driver entry points are not available");
+}
+struct VmmRegion {
+  void* ptr;
+  size_t bytes;
+  CUmemGenericAllocationHandle handle;
+};
+std::mutex g_vmm_mu;
+std::vector<VmmRegion> g_vmm;
+CUmemAllocationProp vmm_prop(int device) {
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  return prop;
+}
+int vmm_map(const Vmm& v, CUmemGenericAllocationHandle h, size_t bytes, int access_device, void** out) {
+  CUdeviceptr va = 0;
+  CUresult r = v.MemAddressReserve(&va, bytes, 0, 0, 0);
+  if (r != CUDA_SUCCESS) return lg_set_error("cuMemAddressReserve(%zu) -> %d", bytes, (int)r);
+  r = v.MemMap(va, bytes, 0, h, 0);
+  if (r != CUDA_SUCCESS) {
+    v.MemAddressFree(va, bytes);
+    return lg_set_error("cuMemMap(%zu) -> %d", bytes, (int)r);
+  }
+  CUmemAccessDesc acc;
+  memset(&acc, 0, sizeof(acc));
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = access_device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  r = v.MemSetAccess(va, bytes, &acc, 1);
+  if (r != CUDA_SUCCESS) {
+    v.MemUnmap(va, bytes);
+    v.MemAddressFree(va, bytes);
+    return lg_set_error("cuMemSetAccess(device %d) -> %d", access_device, (int)r);
+  }
+  *out = (void*)va;
+  std::lock_guard<std::mutex> g(g_vmm_mu);
+  g_vmm.push_back({(void*)va, bytes, h});
+  return 0;
+}
+}  // namespace
+
+extern "C" int64_t lg_vmm_round_up(int64_t bytes) {
+  const int64_t g = 2ll << 20;  // 2 MB: the allocation granularity of device memory on this architecture
+  return (bytes + g - 1) / g * g;
+}
+
+extern "C" int lg_vmm_alloc(int64_t bytes, void** ptr, int32_t* shareable_fd) {
+  LG_REQUIRE(ptr && shareable_fd && bytes > 0, "lg_vmm_alloc: bad argument");
+  Vmm v;
+  int rc = vmm_load(&v);
+  if (rc) return rc;
+  int dev = 0;
+  LG_CUDA(cudaGetDevice(&dev));
+  CUmemAllocationProp prop = vmm_prop(dev);
+  size_t gran = 0;
+  CUresult r = v.MemGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+  if (r != CUDA_SUCCESS || gran == 0) gran = 2u << 20;
+  const size_t len = ((size_t)bytes + gran - 1) / gran * gran;
+  CUmemGenericAllocationHandle h;
+  r = v.MemCreate(&h, len, &prop, 0);
+  if (r != CUDA_SUCCESS) return lg_set_error("cuMemCreate(%zu bytes on device %d) -> %d", len, dev, (int)r);
+  int fd = -1;
+  r = v.MemExport(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+  if (r != CUDA_SUCCESS) {
+    v.MemRelease(h);
+    return lg_set_error("cuMemExportToShareableHandle -> %d", (int)r);
+  }
+  rc = vmm_map(v, h, len, dev, ptr);
+  if (rc) {
+    close(fd);
+    v.MemRelease(h);
+    return rc;
+  }
+  *shareable_fd = fd;
+  return 0;
+}
+
+extern "C" int lg_vmm_import(int32_t shareable_fd, int64_t bytes, void** ptr) {
+  LG_REQUIRE(ptr && shareable_fd >= 0 && bytes > 0, "lg_vmm_import: bad argument");
+  Vmm v;
+  int rc = vmm_load(&v);
+  if (rc) return rc;
+  int dev = 0;
+  LG_CUDA(cudaGetDevice(&dev));
+  CUmemGenericAllocationHandle h;
+  CUresult r = v.MemImport(&h, (void*)(uintptr_t)shareable_fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+  if (r != CUDA_SUCCESS) return lg_set_error("cuMemImportFromShareableHandle(fd %d) -> %d", shareable_fd, (int)r);
+  const size_t len = (size_t)lg_vmm_round_up(bytes);
+  rc = vmm_map(v, h, len, dev, ptr);
+  if (rc) v.MemRelease(h);
+  return rc;
+}
+
+extern "C" int lg_vmm_free(void* ptr) {
+  Vmm v;
+  int rc = vmm_load(&v);
+  if (rc) return rc;
+  VmmRegion reg{nullptr, 0, 0};
+  {
+    std::lock_guard<std::mutex> g(g_vmm_mu);
+    for (size_t i = 0; i < g_vmm.size(); i++)
+      if (g_vmm[i].ptr == ptr) {
+        reg = g_vmm[i];
+        g_vmm.erase(g_vmm.begin() + i);
+        break;
+      }
+  }
+  LG_REQUIRE(reg.ptr, "lg_vmm_free: %p is not a VMM allocation of this library", ptr);
+  v.MemUnmap((CUdeviceptr)reg.ptr, reg.bytes);
+  v.MemAddressFree((CUdeviceptr)reg.ptr, reg.bytes);
+  v.MemRelease(reg.handle);
+  return 0;
+}
+
 extern "C" int lg_device_alloc(void** ptr, int64_t bytes) {
   LG_REQUIRE(ptr && bytes >= 0, "lg_device_alloc: bad argument");
   LG_CUDA(cudaMalloc(ptr, (size_t)(bytes > 0 ? bytes : 1)));

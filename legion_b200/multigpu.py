@@ -34,3 +34,45 @@ def coordinate_train_steps(dist, n_train_local, batch, device=None):
     t = torch.tensor([n_train_local], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return (int(t.item()) - 1) // batch
+
+
+def exchange_fds(dist, fd, rank, kg, tag="0"):
+    """Every rank of a clique owns one file descriptor (the POSIX handle of its VMM cache shard, lg_vmm_alloc) and
+    needs its peers' descriptors.  Descriptors only travel over AF_UNIX sockets (SCM_RIGHTS), so each rank listens on
+    an abstract-namespace socket, serves its descriptor to the kg-1 peers from a helper thread and fetches theirs.
+    Returns the kg descriptors in slot order; the own slot holds `fd` itself.  Received descriptors belong to the
+    caller (close them once imported)."""
+    import os
+    import socket
+    import threading
+    _, j, base = clique_of(rank, kg)
+    port = os.environ.get("MASTER_PORT", "0")
+    name = lambda r: f"\0legion_b200_vmm_{port}_{tag}_{r}"  # noqa: E731  (abstract namespace: nothing to unlink)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(name(rank))
+    srv.listen(kg)
+
+    def serve():
+        for _ in range(kg - 1):
+            c, _a = srv.accept()
+            socket.send_fds(c, [b"fd"], [fd])
+            c.close()
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    dist.barrier()  # every listener is up
+    got = [None] * kg
+    got[j] = fd
+    for slot in range(kg):
+        if slot == j:
+            continue
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.connect(name(base + slot))
+        _msg, fds, _flags, _addr = socket.recv_fds(c, 16, 1)
+        c.close()
+        assert len(fds) == 1, "peer sent no descriptor"
+        got[slot] = fds[0]
+    th.join()
+    srv.close()
+    dist.barrier()
+    return got

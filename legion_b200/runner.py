@@ -55,6 +55,34 @@ class RawDeviceBuffer:
         self.owned = False
         return self
 
+    @classmethod
+    def vmm(cls, nbytes, device):
+        """cuMemCreate-backed memory whose POSIX descriptor other processes map at full page size (cache shards of
+        the one-process-per-GPU deployment; see lg_vmm_alloc)"""
+        self = cls.__new__(cls)
+        self.L = capi.load()
+        self.device = device
+        self.nbytes = int(nbytes)
+        p, fd = C.c_void_p(), C.c_int32(-1)
+        with torch.cuda.device(device):
+            check(self.L.lg_vmm_alloc(self.nbytes, C.byref(p), C.byref(fd)))
+        self.ptr, self.fd = p.value, fd.value
+        self.owned = "vmm"
+        return self
+
+    @classmethod
+    def from_vmm_fd(cls, fd, nbytes, device):
+        self = cls.__new__(cls)
+        self.L = capi.load()
+        self.device = device
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        with torch.cuda.device(device):
+            check(self.L.lg_vmm_import(int(fd), self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.owned = "vmm"
+        return self
+
     def ipc_handle(self):
         h = (C.c_char * 64)()
         check(self.L.lg_ipc_export(C.c_void_p(self.ptr), h))
@@ -73,7 +101,9 @@ class RawDeviceBuffer:
 
     def free(self):
         if self.ptr:
-            if self.owned:
+            if self.owned == "vmm":
+                self.L.lg_vmm_free(C.c_void_p(self.ptr))
+            elif self.owned:
                 self.L.lg_device_free(C.c_void_p(self.ptr))
             else:
                 self.L.lg_ipc_close(C.c_void_p(self.ptr))
@@ -237,7 +267,7 @@ class DataPath:
         directory = torch.empty(self.N, dtype=I32, device=dev)
         check(self.L.lg_fill_i32(st, _ptr(directory), capi.CACHEMISS_FLAG, self.N))
         check(self.L.lg_place_features(st, _ptr(order), cap, kg, self.N, _ptr(directory)))
-        raw = RawDeviceBuffer(cap * self.dim * 4, self.device)
+        raw = self._shard_alloc(cap * self.dim * 4, kg)
         check(self.L.lg_fill_feature_shard(st, _ptr(order), cap, kg, j, self.dim, self.N, C.c_void_p(self._backing),
                                            C.c_void_p(raw.ptr)))
         torch.cuda.current_stream().synchronize()
@@ -259,7 +289,7 @@ class DataPath:
         directory = torch.empty(self.N, dtype=I32, device=dev)
         check(self.L.lg_fill_i32(st, _ptr(directory), capi.CACHEMISS_FLAG, self.N))
         check(self.L.lg_place_features(st, _ptr(order), cap, kg, self.N, _ptr(directory)))
-        raw = RawDeviceBuffer(cap * self.dim * 4, self.device)
+        raw = self._shard_alloc(cap * self.dim * 4, kg)
         check(self.L.lg_synth_feature_shard(st, _ptr(order), cap, kg, j, self.dim, self.N, seed, C.c_void_p(raw.ptr)))
         torch.cuda.current_stream().synchronize()
         shard_ptrs = [0] * kg
@@ -281,12 +311,12 @@ class DataPath:
         directory = torch.empty(self.N, dtype=I32, device=dev)
         check(self.L.lg_fill_i32(st, _ptr(directory), capi.CACHEMISS_FLAG, self.N))
         check(self.L.lg_place_topology(st, _ptr(order), cap, kg, ki, self.N, _ptr(directory)))
-        ip = RawDeviceBuffer((cap + 1) * 8, self.device)
+        ip = self._shard_alloc((cap + 1) * 8, kg)
         full_ip, full_ix = self._full
         check(self.L.lg_topo_shard_indptr(st, _ptr(order), cap, kg, j, self.N, C.c_void_p(full_ip), C.c_void_p(ip.ptr)))
         torch.cuda.current_stream().synchronize()
         total = int(ip.tensor(torch.int64, (cap + 1,))[cap].item())
-        ix = RawDeviceBuffer(max(total, 1) * 4, self.device)
+        ix = self._shard_alloc(max(total, 1) * 4, kg)
         check(self.L.lg_topo_shard_fill(st, _ptr(order), cap, kg, j, self.N, C.c_void_p(full_ip), C.c_void_p(full_ix),
                                         C.c_void_p(ip.ptr), C.c_void_p(ix.ptr)))
         torch.cuda.current_stream().synchronize()
@@ -300,13 +330,40 @@ class DataPath:
         self.topo_shard = (ip, ix, total)
         return directory
 
+    def _shard_alloc(self, nbytes, kg):
+        """cache shards that peers in OTHER processes will map are VMM allocations: a legacy cudaIpcOpenMemHandle
+        mapping is read through small pages and random row reads out of a multi-GB peer shard collapse to ~90 GB/s
+        (profiles/r01b_peer_mapping.md).  LG_SHARD_IPC=legacy keeps the reference's cudaIpc handles."""
+        import os
+        if kg > 1 and os.environ.get("LG_SHARD_IPC", "vmm") != "legacy":
+            return RawDeviceBuffer.vmm(nbytes, self.device)
+        return RawDeviceBuffer(nbytes, self.device)
+
     def _exchange(self, raw, nbytes, kg, j, dist, nbytes_own=None):
-        """all-gather CUDA IPC handles of one buffer per clique member; returns the kg device pointers"""
-        from .multigpu import exchange_handles
+        """one buffer per clique member -> the kg device pointers, own slot first-hand, peers mapped: VMM descriptors
+        passed over AF_UNIX sockets, or (LG_SHARD_IPC=legacy) all-gathered CUDA IPC handles"""
+        from .multigpu import exchange_fds, exchange_handles
         assert dist is not None and dist.is_initialized(), "multi-GPU cache needs torch.distributed"
-        mine = (raw.ipc_handle(), nbytes if nbytes is not None else nbytes_own)
-        clique = exchange_handles(dist, mine, self.rank, kg)
+        own_bytes = nbytes if nbytes is not None else nbytes_own
+        self._xchg = getattr(self, "_xchg", 0) + 1
         ptrs = []
+        if raw.owned == "vmm":
+            import os
+            sizes = exchange_handles(dist, own_bytes, self.rank, kg)
+            fds = exchange_fds(dist, raw.fd, self.rank, kg, tag=str(self._xchg))
+            for p in range(kg):
+                if p == j:
+                    ptrs.append(raw.ptr)
+                else:
+                    peer = RawDeviceBuffer.from_vmm_fd(fds[p], sizes[p], self.device)
+                    os.close(fds[p])
+                    self._keep.append(peer)
+                    ptrs.append(peer.ptr)
+            dist.barrier()  # every import is done before anyone may close its exported descriptor
+            os.close(raw.fd)
+            raw.fd = -1
+            return ptrs
+        clique = exchange_handles(dist, (raw.ipc_handle(), own_bytes), self.rank, kg)
         for p in range(kg):
             if p == j:
                 ptrs.append(raw.ptr)

@@ -37,7 +37,17 @@ def _worker(rank, world, port, out):
     hot = torch.zeros(N, dtype=torch.int64)
     hot[torch.from_numpy(mine.astype(np.int64))] += 1
     multigpu.aggregate_hotness(dist, hot, rank, world)
-    out[rank] = dict(steps=steps, got=got, hot=hot.numpy().copy(), n=len(mine), ids=mine.copy())
+    # descriptor exchange (what carries the VMM shard handles): every rank passes an open pipe's read end
+    rd, wr = os.pipe()
+    os.write(wr, bytes([65 + rank]) * 4)
+    fds = multigpu.exchange_fds(dist, rd, rank, world, tag="t")
+    seen = [os.read(fds[p], 4) if p != rank else b"" for p in range(world)]
+    for p in range(world):
+        if p != rank:
+            os.close(fds[p])
+    os.close(rd)
+    os.close(wr)
+    out[rank] = dict(steps=steps, got=got, hot=hot.numpy().copy(), n=len(mine), ids=mine.copy(), seen=seen)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,6 +66,7 @@ def test_two_rank_host_logic(oracle):
     assert r0["steps"] == r1["steps"] == want_steps
     for r in (r0, r1):
         assert [g[0][0] for g in r["got"]] == [0, 1] and [g[1] for g in r["got"]] == [1000, 1001]
+    assert r0["seen"] == [b"", b"BBBB"] and r1["seen"] == [b"AAAA", b""]  # each rank read its peer's pipe through the passed fd
     want_hot = np.bincount(train, minlength=5000)
     assert np.array_equal(r0["hot"], want_hot) and np.array_equal(r1["hot"], want_hot)
     # both ranks derive the same ranking -> the same interleaved placement (rank r -> GPU r % Kg, row r / Kg)
