@@ -142,6 +142,8 @@ int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);
 
 /* diagnostics: per-tile phase timestamps of the sampler kernels (globaltimer ns, clock64) written to a device
  * buffer of lg_debug_trace_words() u64 words, layout [(hop-1)*2 + kernel][tile < 2048][phase < 8][2]; NULL = off */
+/* diagnostics: `ctas` x `threads` spinning for `cycles` SM clocks without touching memory */
+int lg_debug_spin(lg_stream_t stream, int32_t ctas, int32_t threads, int64_t cycles);
 int lg_debug_set_trace(lg_sampler* s, unsigned long long* device_buf);
 int64_t lg_debug_trace_words(void);
 

@@ -54,6 +54,7 @@ _PROTOS = {
     "lg_sampler_set_gather_variant": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_overlap": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_gather_fusion": (C.c_int, [vp, C.c_int32]),
+    "lg_debug_spin": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int64]),
     "lg_debug_set_trace": (C.c_int, [vp, vp]),
     "lg_debug_trace_words": (C.c_int64, []),
     "lg_batch_wait": (C.c_int, [vp, vp, C.POINTER(Batch)]),

@@ -32,6 +32,8 @@ struct GatherArgs {
   u64* tier;           // [3] local / peer / miss rows, may be null
   int32_t* status;
   int32_t l2;          // lg_l2_hints()
+  int32_t* ticket;     // [2] zeroed: tiles are claimed dynamically (robust to CTAs that start late or run slowed down next to
+                       // another kernel); null = static round-robin over the grid
 };
 
 __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int64_t* cnt) {
@@ -187,10 +189,15 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-constexpr int kTmaRows = 32;  // rows per stage == lanes
+// Rows per stage (tile) of one single-warp CTA.  Every row is its own bulk copy, and the compiler serialises a
+// per-thread cp.async.bulk over the active lanes (ELECT / R2UR x3 / UBLKCP / loop: ~8 dependent-latency instructions
+// per row), so a 32-row tile keeps its warp busy issuing for >1000 cycles.  Alone that is still 2x faster than DRAM,
+// but next to ANY other resident warp (one spinning warp per SM is enough, profiles/r01b_overlap.md) the issue loop
+// becomes the bottleneck and the gather loses a third of its bandwidth.  Smaller tiles spread the same rows in flight
+// over more warps (8-row tiles: 16 warps per SM, 4 per scheduler), so the issue chains interleave.
 // Pipeline: iteration `it` fills stage it % STAGES with tile(it) and drains tile(it - LAG),
 // LAG = STAGES - 2: LAG tiles of row loads in flight, one stage being stored, one being refilled.
-template <int STAGES>
+template <int STAGES, int kTmaRows>
 __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   static_assert(STAGES >= 3, "need a stage in store and a stage in refill besides the loads in flight");
   constexpr int LAG = STAGES - 2;
@@ -212,15 +219,29 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   }
   __syncwarp();
   int32_t t0 = 0, t1 = 0, t2 = 0;
-  int64_t my_tiles = 0;
-  if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  __shared__ int64_t s_tileidx[STAGES];
+
+  // Tile order.  Static: tile(it) = blockIdx.x + it * gridDim.x.  Dynamic (a.ticket): tiles are claimed from a global
+  // counter, two iterations ahead of their row loads — a CTA that starts late (its SM still busy with another
+  // kernel's CTAs) or whose warp gets fewer issue slots simply ends up moving fewer tiles, instead of holding the
+  // whole launch back with a fixed share.  Claims are monotone: once one fails, every later one fails too.
+  auto claim = [&](int64_t it) -> int64_t {
+    int64_t t;
+    if (a.ticket) {
+      int32_t c = 0;
+      if (lane == 0) c = atomicAdd(a.ticket, 1);
+      t = __shfl_sync(0xffffffffu, c, 0);
+    } else {
+      t = blockIdx.x + it * (int64_t)gridDim.x;
+    }
+    return t < n_tiles ? t : -1;
+  };
 
   // The id -> directory -> pointer chain is software-pipelined so that no iteration waits on it:
   // ids are loaded two tiles ahead, directory entries one tile ahead, pointers are formed at use.
-  auto load_id = [&](int64_t it) -> int32_t {
-    const int64_t tile = blockIdx.x + it * gridDim.x;
+  auto load_id = [&](int64_t tile) -> int32_t {
     const int64_t r = tile * kTmaRows + lane;
-    if (it >= my_tiles || r >= cnt) return -1;
+    if (tile < 0 || lane >= kTmaRows || r >= cnt) return -1;
     if (off + r >= a.dst_rows) {
       *a.status = 2;
       return -1;
@@ -246,13 +267,17 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
     if (didx == a.local_part) t0++; else t1++;
     return a.cache.shard[didx] + (int64_t)fidx * a.cache.dim;
   };
-  int32_t id0 = load_id(0), id1 = load_id(1);
+  int64_t tile0 = claim(0);
+  int64_t tile1 = tile0 >= 0 ? claim(1) : -1;
+  int32_t id0 = load_id(tile0), id1 = load_id(tile1);
   int32_t loc0 = load_loc(id0);
-  for (int64_t it = 0; it < my_tiles + LAG; it++) {
-    const int32_t id2 = load_id(it + 2);
+  int64_t n_issued = 0;  // tiles whose loads this CTA issued; the drain runs LAG iterations behind
+  for (int64_t it = 0; tile0 >= 0 || it < n_issued + LAG; it++) {
+    const int64_t tile2 = tile1 >= 0 ? claim(it + 2) : -1;
+    const int32_t id2 = load_id(tile2);
     const int32_t loc1 = load_loc(id1);
     const float* src = form_ptr(id0, loc0);
-    if (it < my_tiles) {
+    if (tile0 >= 0) {
       const int s = (int)(it % STAGES);
       // stage s was read by the store of tile(it - STAGES), issued two iterations ago: only the
       // store issued in the previous iteration may still be reading shared memory
@@ -262,25 +287,29 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
       const uint32_t bar = smem_u32(&bars[s]);
       if (lane == 0) {
         s_valid[s] = valid;
+        s_tileidx[s] = tile0;
         mbar_expect_tx(bar, row_bytes * (uint32_t)__popc(valid));
       }
       __syncwarp();
       if (src) bulk_g2s(smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), src, row_bytes, bar, pol_ld);
+      n_issued = it + 1;
     }
+    tile0 = tile1;
+    tile1 = tile2;
     id0 = id1;
     id1 = id2;
     loc0 = loc1;
     const int64_t dt = it - LAG;
-    if (dt >= 0 && dt < my_tiles) {
+    if (dt >= 0 && dt < n_issued) {
       const int s = (int)(dt % STAGES);
       const uint32_t parity = (uint32_t)((dt / STAGES) & 1);
-      const int64_t tile = blockIdx.x + dt * gridDim.x;
+      const int64_t tile = s_tileidx[s];
       const int64_t row0 = off + tile * kTmaRows;
       const unsigned valid = s_valid[s];
       mbar_wait(smem_u32(&bars[s]), parity);
       const int64_t left = cnt - tile * kTmaRows;
       const int rows_here = left < kTmaRows ? (int)left : kTmaRows;
-      const unsigned want = (rows_here >= 32) ? 0xffffffffu : ((1u << rows_here) - 1u);
+      const unsigned want = (rows_here >= 32) ? 0xffffffffu : ((1u << rows_here) - 1u);  // lanes >= kTmaRows never hold a row
       if (valid == want) {
         // every row of the tile is present: the destination rows are contiguous -> ONE bulk store
         if (lane == 0) bulk_s2g(a.dst + row0 * a.cache.dim, smem_u32(smem + (size_t)s * stage_bytes),
@@ -295,38 +324,55 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tier_flush(a, t0, t1, t2, lane);
+  if (a.ticket && lane == 0) {  // the last CTA out re-arms the counters for the next launch on this stream
+    if (atomicAdd(a.ticket + 1, 1) == (int32_t)gridDim.x - 1) {
+      a.ticket[0] = 0;
+      a.ticket[1] = 0;
+    }
+  }
 }
 
 // tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {4,8}, LG_TMA_STAGES {3,4,6},
 // LG_LDG_CTAS resident CTAs per SM assumed when sizing the LDG grid
 struct Tune {
-  int ldg_r, tma_stages, ldg_ctas, tma_ctas;
+  int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows;
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 3, 8, 4};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
+    Tune x{8, 3, 8, 4, 32};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
     if (const char* e = getenv("LG_LDG_CTAS")) x.ldg_ctas = atoi(e);
-    if (const char* e = getenv("LG_TMA_CTAS")) x.tma_ctas = atoi(e);  // cap on resident gather CTAs per SM (smem left for the sampler)
+    if (const char* e = getenv("LG_TMA_CTAS")) x.tma_ctas = atoi(e);
+    if (const char* e = getenv("LG_TMA_ROWS")) x.tma_rows = atoi(e);  // rows per tile of a single-warp CTA: 8, 16 or 32  // cap on resident gather CTAs per SM (smem left for the sampler)
     return x;
   }();
   return t;
 }
 
-template <int STAGES>
+template <int STAGES, int ROWS>
 int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
-  const size_t smem = (size_t)a.cache.dim * 4 * kTmaRows * STAGES;
-  LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)a.cache.dim * 4 * ROWS * STAGES;
+  LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (ctas_per_sm > tune().tma_ctas) ctas_per_sm = tune().tma_ctas;
+  const int cap = tune().tma_ctas * (32 / ROWS);  // the cap is stated for 32-row tiles: same bytes in flight per SM
+  if (ctas_per_sm > cap) ctas_per_sm = cap;
+  if (ctas_per_sm > 24) ctas_per_sm = 24;  // leave CTA slots (32 per SM) to the sampler
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  int64_t tiles = (max_rows + kTmaRows - 1) / kTmaRows;
+  int64_t tiles = (max_rows + ROWS - 1) / ROWS;
   int64_t grid = (int64_t)kSMs * ctas_per_sm;
   if (tiles < grid) grid = tiles > 0 ? tiles : 1;
-  gather_tma_kernel<STAGES><<<(int)grid, 32, smem, st>>>(a);
+  gather_tma_kernel<STAGES, ROWS><<<(int)grid, 32, smem, st>>>(a);
   LG_LAUNCH_OK();
   return 0;
+}
+template <int STAGES>
+int launch_tma_rows(cudaStream_t st, const GatherArgs& a, int64_t max_rows, int rows) {
+  switch (rows) {
+    case 8: return launch_tma<STAGES, 8>(st, a, max_rows);
+    case 16: return launch_tma<STAGES, 16>(st, a, max_rows);
+    default: return launch_tma<STAGES, 32>(st, a, max_rows);
+  }
 }
 
 template <int R>
@@ -349,13 +395,15 @@ int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) 
   const bool vec_ok = (dim % 4 == 0) && (((uintptr_t)a.dst & 15) == 0) && (((uintptr_t)a.cache.backing & 15) == 0);
   const Tune& t = tune();
   if (variant == LG_GATHER_AUTO) variant = LG_GATHER_TMA;  // falls through to LDG when rows are not 16-byte multiples
-  if (variant == LG_GATHER_TMA && vec_ok && (size_t)dim * 4 * kTmaRows * 3 <= 200 * 1024) {
+  int rows = (t.tma_rows == 8 || t.tma_rows == 16) ? t.tma_rows : 32;
+  while (rows > 8 && (size_t)dim * 4 * rows * 3 > 200 * 1024) rows >>= 1;  // very wide rows: smaller tiles
+  if (variant == LG_GATHER_TMA && vec_ok && (size_t)dim * 4 * rows * 3 <= 200 * 1024) {
     int stages = t.tma_stages;
-    while (stages > 3 && (size_t)dim * 4 * kTmaRows * stages > 200 * 1024) stages--;
+    while (stages > 3 && (size_t)dim * 4 * rows * stages > 200 * 1024) stages--;
     switch (stages) {
-      case 4: return launch_tma<4>(st, a, max_rows);
-      case 6: return launch_tma<6>(st, a, max_rows);
-      default: return launch_tma<3>(st, a, max_rows);
+      case 4: return launch_tma_rows<4>(st, a, max_rows, rows);
+      case 6: return launch_tma_rows<6>(st, a, max_rows, rows);
+      default: return launch_tma_rows<3>(st, a, max_rows, rows);
     }
   }
   if (t.ldg_r == 4) return launch_ldg<4>(st, a, max_rows, vec_ok);
@@ -404,6 +452,7 @@ extern "C" int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, 
   a.tier = (u64*)tier_rows;
   a.status = s->status;
   a.l2 = lg_l2_hints();
+  a.ticket = s->gather_ticket;
   LG_REQUIRE(a.hop <= s->n_hops, "lg_feature_cache_lookup: op_id %d beyond %d hops", op_id, s->n_hops);
   int64_t max_rows = 0;
   for (int h = first_hop; h <= a.hop; h++) max_rows += s->slots_per_hop[h];
@@ -433,5 +482,6 @@ extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache,
   a.tier = (u64*)tier_rows;
   a.status = dummy_status;
   a.l2 = lg_l2_hints();
+  a.ticket = nullptr;  // no handle to own a counter: static tile order
   return launch_gather((cudaStream_t)stream, a, variant, n);
 }

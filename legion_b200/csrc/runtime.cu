@@ -387,3 +387,24 @@ extern "C" int lg_device_mem_info(int64_t* free_bytes, int64_t* total_bytes) {
   if (total_bytes) *total_bytes = (int64_t)t;
   return 0;
 }
+
+// diagnostics: a kernel that only spins (no memory traffic) — scripts/overlap_probe.py uses it to tell SM-side
+// contention from memory-side contention next to the gather
+__global__ void lg_spin_kernel(long long cycles, int* sink) {
+  const long long t0 = clock64();
+  int x = threadIdx.x;
+  while (clock64() - t0 < cycles) x = x * 1664525 + 1013904223;
+  if (x == 0x7fffffff && sink) *sink = x;
+}
+extern "C" int lg_debug_spin(lg_stream_t stream, int32_t ctas, int32_t threads, int64_t cycles) {
+  static int carve = [] {
+    const char* e = getenv("LG_SPIN_CARVEOUT");
+    int v = e ? atoi(e) : -1;
+    if (v >= 0) cudaFuncSetAttribute(lg_spin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    return v;
+  }();
+  (void)carve;
+  lg_spin_kernel<<<ctas, threads, 0, (cudaStream_t)stream>>>((long long)cycles, nullptr);
+  LG_LAUNCH_OK();
+  return 0;
+}

@@ -597,6 +597,30 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// Shared-memory carve-out of the sampler kernels (LG_CARVEOUT=<percent>, default -1 = the driver's choice).
+// An SM's unified L1/shared array is configured per resident kernel; the gather needs ~160 KB of shared memory per
+// SM, and an SM that holds even ONE CTA of a kernel configured for a small carve-out cannot take the gather's CTAs
+// until it has drained (one spinning warp per SM stretches the gather from 0.135 to 0.200 ms; with the spinner's
+// carve-out at 100 % the gather is unaffected).  Forcing 100 % on the sampler kernels was measured and REJECTED: their
+// L1 shrinks to ~28 KB, hop 2 slows from 0.100 to 0.137 ms, and the pipelined step gets worse (0.252 vs 0.227 ms) —
+// next to the real sampler the gather is slowed by something else than CTA placement (profiles/r01b_overlap.md).
+static int carveout_pct() {
+  static int v = [] {
+    const char* e = getenv("LG_CARVEOUT");
+    return e ? atoi(e) : -1;
+  }();
+  return v;
+}
+#define LG_CARVEOUT(kernel)                                                                            \
+  do {                                                                                                 \
+    static bool done_ = false;                                                                         \
+    if (!done_) {                                                                                      \
+      done_ = true;                                                                                    \
+      if (carveout_pct() >= 0)                                                                         \
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct()); \
+    }                                                                                                  \
+  } while (0)
+
 extern "C" int64_t lg_num_ids(int32_t batch_size, const int32_t* fanout, int32_t n_hops) {
   int64_t tot = batch_size, per = batch_size;  // engine/server.cu:187-199
   for (int i = 0; i < n_hops; i++) {
@@ -701,6 +725,13 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_CUDA(cudaMalloc(&s->status, sizeof(int32_t)));
   LG_CUDA(cudaMemset(s->status, 0, sizeof(int32_t)));
   if (s->hashed) LG_CUDA(cudaMalloc(&s->seed_local, (size_t)max_batch * sizeof(int32_t)));
+  {
+    const char* e = getenv("LG_GATHER_DYNAMIC");
+    if (e && atoi(e) != 0) {  // opt-in: measured neutral to slightly negative (profiles/r01b_overlap.md)
+      LG_CUDA(cudaMalloc(&s->gather_ticket, 2 * sizeof(int32_t)));
+      LG_CUDA(cudaMemset(s->gather_ticket, 0, 2 * sizeof(int32_t)));
+    }
+  }
   LG_CUDA(cudaMallocHost(&s->pinned_seeds, (size_t)max_batch * 2 * sizeof(int32_t)));
   LG_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   for (int h = 0; h <= LG_MAX_HOPS; h++) LG_CUDA(cudaEventCreateWithFlags(&s->ev_fork[h], cudaEventDisableTiming));
@@ -717,6 +748,7 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaFree(s->pm);
   cudaFree(s->table);
   cudaFree(s->seed_local);
+  cudaFree(s->gather_ticket);
   cudaFree(s->gid[0]);
   cudaFree(s->gid[1]);
   cudaFree(s->small);
@@ -812,6 +844,7 @@ extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
 // the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
 static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
   if (!s->hashed) {  // HASHED: the table is re-initialised by the next lg_batch_generate instead
+    LG_CARVEOUT((pm_clear_kernel));
     pm_clear_kernel<<<kSMs * 4, kBlock, 0, st>>>(b->ids, b->node_counter, s->pm, lg_l2_hints());
     LG_LAUNCH_OK();
   }
@@ -849,12 +882,16 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   if (size < 0) size = 0;
   int grid = size > 0 ? (size + kBlock - 1) / kBlock : 1;
   if (s->hashed) {
+    LG_CARVEOUT((batch_generate_kernel<true>));
     batch_generate_kernel<true><<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
                                                          b->labels, b->node_counter, b->edge_counter, map_of(s), lg_l2_hints());
+    LG_CARVEOUT((seed_local_kernel));
     seed_local_kernel<<<grid, kBlock, 0, st>>>(b->ids, b->node_counter, s->seed_local, map_of(s), lg_l2_hints());
-  } else
+  } else {
+    LG_CARVEOUT((batch_generate_kernel<false>));
     batch_generate_kernel<false><<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
                                                           b->labels, b->node_counter, b->edge_counter, map_of(s), lg_l2_hints());
+  }
   LG_LAUNCH_OK();
   s->pm_dirty = 1;
   s->dirty_batch = *b;
@@ -864,10 +901,10 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
 template <int RNG, bool HASHED>
 static void launch_sample(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
   switch (tile_f) {
-    case 256: sample_hop_kernel<256, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
-    case 128: sample_hop_kernel<128, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
-    case 64: sample_hop_kernel<64, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
-    default: sample_hop_kernel<32, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    case 256: LG_CARVEOUT((sample_hop_kernel<256, RNG, HASHED>)); sample_hop_kernel<256, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    case 128: LG_CARVEOUT((sample_hop_kernel<128, RNG, HASHED>)); sample_hop_kernel<128, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    case 64: LG_CARVEOUT((sample_hop_kernel<64, RNG, HASHED>)); sample_hop_kernel<64, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    default: LG_CARVEOUT((sample_hop_kernel<32, RNG, HASHED>)); sample_hop_kernel<32, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
   }
 }
 
@@ -929,19 +966,22 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   r.status = s->status;
   r.trace = s->trace;
   if (s->hashed) {
-    if (s->rank_items[h] == 8) rank_kernel<8, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
-    else rank_kernel<4, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+    if (s->rank_items[h] == 8) { LG_CARVEOUT((rank_kernel<8, true>)); rank_kernel<8, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
+    else { LG_CARVEOUT((rank_kernel<4, true>)); rank_kernel<4, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
   } else {
-    if (s->rank_items[h] == 8) rank_kernel<8, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
-    else rank_kernel<4, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r);
+    if (s->rank_items[h] == 8) { LG_CARVEOUT((rank_kernel<8, false>)); rank_kernel<8, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
+    else { LG_CARVEOUT((rank_kernel<4, false>)); rank_kernel<4, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
   }
   LG_LAUNCH_OK();
   if (relabel_own) {
     const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
-    if (s->hashed)
+    if (s->hashed) {
+      LG_CARVEOUT((relabel_kernel<true>));
       relabel_kernel<true><<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, map_of(s), lg_l2_hints());
-    else
+    } else {
+      LG_CARVEOUT((relabel_kernel<false>));
       relabel_kernel<false><<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, map_of(s), lg_l2_hints());
+    }
     LG_LAUNCH_OK();
   }
   return 0;
@@ -969,6 +1009,7 @@ extern "C" int lg_io_complete(lg_sampler* s, lg_stream_t stream_, int32_t mode, 
   LG_REQUIRE(s && b, "lg_io_complete: null argument");
   cudaStream_t st = (cudaStream_t)stream_;
   if (mode == LG_TRAINMODE && node_hotness) {  // :558
+    LG_CARVEOUT((hotness_measure_kernel));
     hotness_measure_kernel<<<kSMs * 2, kBlock, 0, st>>>(b->ids, b->node_counter, (u64*)node_hotness, max_ids);
     LG_LAUNCH_OK();
   }

@@ -39,6 +39,7 @@ struct lg_sampler {
   int32_t sample_tile_f[LG_MAX_HOPS];
   int32_t rank_tiles[LG_MAX_HOPS];
   int32_t* status;       // device int32: 1 = ids overflow, 2 = features buffer overflow
+  int32_t* gather_ticket;  // [2] dynamic tile claims of the gather (re-armed by the kernel itself)
   int32_t* pinned_seeds;
   // gather/sampling overlap inside lg_run_batch: the gather of hop h runs on `side` while hop h+1
   // is sampled on the caller's stream (the reference's stream-1 / stream-0 split, server.cu:311-317)

@@ -27,7 +27,18 @@ dp.set_overlap(0); dp.set_gather_fusion(2)
 bg = dp.alloc_batch()            # prepared batch for the gather-only stream
 dp.run_once(dp.params(d_train, d_lab, B, 0, seed=1, batch_id=0), bg); torch.cuda.synchronize()
 rows = int(bg.node_counter[9 + H].item())
-dp2 = DataPath(0, fanout, B, N, D); dp2.share_storage_from(dp); dp2.set_overlap(0)
+SMALL = float(os.environ.get("SAMPLER_SCALE", "1.0"))
+if SMALL < 1.0:  # the sampler walks its own, smaller graph (L2-resident topology): separates DRAM from L2/SM contention
+    class A2: workload = "products"; scale = SMALL; batch = 0
+    sh2 = bench.shape_of(A2)
+    ip2, ix2, _f2, lab2, E2 = bench.device_dataset(dict(sh2, dense=False), 0)
+    tr2 = bench.train_split(sh2, 1)[0]
+    d_train = torch.from_numpy(tr2).to(dev); d_lab = lab2[d_train.long()].contiguous()
+    steps = (len(tr2) - 1) // B
+    dp2 = DataPath(0, fanout, B, sh2["N"], D); dp2.set_full_graph(ip2.data_ptr(), ix2.data_ptr(), keep=[ip2, ix2]); dp2.set_overlap(0)
+    print("sampler graph: N", sh2["N"], "E", E2, "topology MB", (E2 * 4 + sh2["N"] * 8) / 1e6)
+else:
+    dp2 = DataPath(0, fanout, B, N, D); dp2.share_storage_from(dp); dp2.set_overlap(0)
 bs = dp2.alloc_batch(feature_rows=1)
 S1, S2 = torch.cuda.Stream(), torch.cuda.Stream()
 n = int(os.environ.get("N_ITERS", "100"))
@@ -59,3 +70,40 @@ print("rows", rows, "alg GB", rows * (8 * D + 8) / 1e9)
 print("alone   ", timed([("sampler", S1, sampler)]), timed([("gather", S2, gather)]))
 print("together", timed([("sampler", S1, sampler), ("gather", S2, gather)]))
 print("alone   ", timed([("sampler", S1, sampler)]), timed([("gather", S2, gather)]))
+
+# ---- what kind of neighbour slows the gather down? ----
+S3 = torch.cuda.Stream()
+xa = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16); xb = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16)
+small = torch.randn(1 << 20, device=dev)            # 4 MB: L2-resident elementwise traffic
+big = torch.randn(1 << 28, device=dev)              # 1 GB: DRAM streaming
+idx = torch.randint(0, 1 << 28, (1 << 21,), device=dev)   # 2 M random 4-byte reads out of 1 GB
+def matmul(k):
+    with torch.cuda.stream(S3):
+        for _ in range(k): torch.mm(xa, xb)
+def l2_elementwise(k):
+    with torch.cuda.stream(S3):
+        for _ in range(k * 8): small.mul_(1.0001)
+def dram_stream(k):
+    with torch.cuda.stream(S3):
+        for _ in range(k): big[: 1 << 25].mul_(1.0001)   # 128 MB read + 128 MB written per call
+def random_reads(k):
+    with torch.cuda.stream(S3):
+        for _ in range(k * 2): big[idx]
+for name, fn in (("bf16 matmul 4096^3", matmul), ("L2-resident elementwise", l2_elementwise), ("DRAM streaming 256 MB/iter", dram_stream),
+                 ("2x2M random 4-byte reads/iter", random_reads)):
+    fn(3); torch.cuda.synchronize()
+    print(name.ljust(32), "alone", timed([("other", S3, fn)]), "with gather", timed([("other", S3, fn), ("gather", S2, gather)]))
+
+# spinning neighbours: no memory traffic at all, varying SM occupancy; one long launch per gather iteration
+for ctas, thr in ((1, 32), (148, 32), (148 * 4, 256), (148 * 8, 256)):
+    def spin(k, ctas=ctas, thr=thr):
+        for _ in range(k):
+            capi.check(dp.L.lg_debug_spin(C.c_void_p(S3.cuda_stream), ctas, thr, 250000))   # ~0.13 ms at 1.9 GHz
+    spin(3); torch.cuda.synchronize()
+    print(f"spin {ctas}x{thr}".ljust(32), "alone", timed([("other", S3, spin)]), "with gather", timed([("other", S3, spin), ("gather", S2, gather)]))
+# many short launches of an empty-ish kernel
+def tiny(k):
+    for _ in range(k * 27):
+        capi.check(dp.L.lg_debug_spin(C.c_void_p(S3.cuda_stream), 148, 128, 2000))
+tiny(3); torch.cuda.synchronize()
+print("27 tiny launches/iter".ljust(32), "alone", timed([("other", S3, tiny)]), "with gather", timed([("other", S3, tiny), ("gather", S2, gather)]))
