@@ -335,16 +335,17 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
 // tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {4,8}, LG_TMA_STAGES {3,4,6},
 // LG_LDG_CTAS resident CTAs per SM assumed when sizing the LDG grid
 struct Tune {
-  int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows;
+  int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows, carveout;
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 3, 8, 4, 32};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
+    Tune x{8, 3, 8, 4, 32, -1};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
     if (const char* e = getenv("LG_LDG_CTAS")) x.ldg_ctas = atoi(e);
     if (const char* e = getenv("LG_TMA_CTAS")) x.tma_ctas = atoi(e);
-    if (const char* e = getenv("LG_TMA_ROWS")) x.tma_rows = atoi(e);  // rows per tile of a single-warp CTA: 8, 16 or 32  // cap on resident gather CTAs per SM (smem left for the sampler)
+    if (const char* e = getenv("LG_TMA_ROWS")) x.tma_rows = atoi(e);
+    if (const char* e = getenv("LG_GATHER_CARVEOUT")) x.carveout = atoi(e);  // preferred smem carve-out (%) of the TMA gather  // rows per tile of a single-warp CTA: 8, 16 or 32  // cap on resident gather CTAs per SM (smem left for the sampler)
     return x;
   }();
   return t;
@@ -354,6 +355,8 @@ template <int STAGES, int ROWS>
 int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
   const size_t smem = (size_t)a.cache.dim * 4 * ROWS * STAGES;
   LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (tune().carveout >= 0)
+    LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES, ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().carveout));
   int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
   const int cap = tune().tma_ctas * (32 / ROWS);  // the cap is stated for 32-row tiles: same bytes in flight per SM
   if (ctas_per_sm > cap) ctas_per_sm = cap;
