@@ -3,11 +3,33 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/legion_b200.h"
 
 int lg_set_error(const char* fmt, ...);
 int lg_l2_hints();  // LG_L2_HINTS bitmask (see the L2 eviction-priority helpers below)
+int lg_pdl();       // LG_PDL (default 1): launch the per-batch kernel chain with programmatic stream serialization
+
+// kernel launch of the per-batch chain: cudaLaunchKernelEx, with the PDL attribute when enabled
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lg_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (lg_pdl()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 #define LG_CUDA(expr)                                                                       \
   do {                                                                                      \
@@ -71,6 +93,17 @@ __device__ __forceinline__ int32_t pick_neighbor(uint32_t slot, int32_t deg, uin
   if (RNG == LG_RNG_MINSTD) return pick_minstd(slot, deg);
   uint32_t r = philox_word0(slot, hop, batch_id, stream_id, k0, k1);
   return (int32_t)__umulhi(r, (uint32_t)deg);
+}
+
+// ---- programmatic dependent launch (PDL).  Every kernel of the per-batch chain starts with pdl_prologue(): it lets the
+//      NEXT kernel of the stream become resident right away (griddepcontrol.launch_dependents) and then waits until
+//      every kernel before it has completed and flushed (griddepcontrol.wait).  The successor is only dispatched once
+//      ALL CTAs of this grid have started, and it blocks in its own wait until this grid is done, so the chain keeps
+//      stream order for memory; what disappears is the launch latency between dependent kernels.  Without the launch
+//      attribute (LG_PDL=0, or a kernel launched with <<<>>>) both instructions are no-ops. ----
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---- relaxed gpu-scope 64-bit accesses (cross-CTA flags and dedup-table words) ----

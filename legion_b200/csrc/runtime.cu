@@ -21,6 +21,14 @@ int lg_l2_hints() {  // see common.cuh; read once
   return v;
 }
 
+int lg_pdl() {  // see common.cuh; read once
+  static int v = [] {
+    const char* e = getenv("LG_PDL");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 int lg_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

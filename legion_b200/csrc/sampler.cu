@@ -189,9 +189,14 @@ template <bool HASHED>
 __global__ void __launch_bounds__(kBlock) batch_generate_kernel(
     const int32_t* __restrict__ all_ids, const int32_t* __restrict__ all_labels, int32_t total_cap,
     int32_t size, int32_t counter, int32_t hop_num, int32_t* __restrict__ ids, int32_t* __restrict__ labels,
-    int32_t* __restrict__ nc, int32_t* __restrict__ ec, const DedupMap map, int32_t l2) {
+    int32_t* __restrict__ nc, int32_t* __restrict__ ec, const DedupMap map, u64* __restrict__ small,
+    int32_t small_words, int32_t l2) {
+  pdl_prologue();
   const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // reset of the per-batch scan state (tickets + tile aggregates), a few KB: done here instead of a memset node so
+  // that the whole chain is kernel -> kernel (the reference memsets an N/8-byte bitmap at this point, :151)
+  for (int32_t i = idx; i < small_words; i += gridDim.x * blockDim.x) small[i] = 0ull;
   if (blockIdx.x == 0 && threadIdx.x < LG_COUNTER_SLOTS) {
     int t = threadIdx.x;
     int32_t v = 0;
@@ -219,6 +224,7 @@ __global__ void __launch_bounds__(kBlock) batch_generate_kernel(
 // later hops read the previous hop's relabelled agg_src.
 __global__ void __launch_bounds__(kBlock) seed_local_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ nc,
                                                             int32_t* __restrict__ seed_local, const DedupMap map, int32_t l2) {
+  pdl_prologue();
   const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc[1]) return;
@@ -253,8 +259,8 @@ struct SampleArgs {
   u64* trace;
 };
 
-template <int TILE_F, int RNG, bool HASHED>
-__global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) {
+template <int TILE_F, int RNG, bool HASHED, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleArgs a) {
   static_assert(TILE_F <= kBlock, "one thread per frontier entry of the tile");
   __shared__ long long s_start[TILE_F];
   __shared__ const int32_t* s_indices[TILE_F];
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(kBlock) sample_hop_kernel(const SampleArgs a) 
 
   constexpr int U = HASHED ? kSlotUnrollHashed : kSlotUnroll;  // slots in flight per thread
   const int tid = threadIdx.x;
+  pdl_prologue();
   if (tid == 0) s_tile = atomicAdd(&a.hs->sample_ticket, 1);
   const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0), once = l2_policy((a.l2 & 8) ? 2 : 0);
   const bool first_hop = (a.hop == 1);
@@ -448,13 +455,14 @@ struct RankArgs {
   u64* trace;
 };
 
-template <int ITEMS, bool HASHED>
-__global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
+template <int ITEMS, bool HASHED, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) rank_kernel(const RankArgs a) {
   static_assert(ITEMS % 4 == 0, "edges are loaded as int4");
   constexpr int TILE = kBlock * ITEMS;
   __shared__ int32_t s_red[kBlock / 32];
   __shared__ int32_t s_tile, s_last;
   const int tid = threadIdx.x;
+  pdl_prologue();
   const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0);
   if (tid == 0) s_tile = atomicAdd(&a.hs->rank_ticket, 1);
   const int32_t E = a.ec[2];
@@ -552,6 +560,7 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
 template <bool HASHED>
 __global__ void __launch_bounds__(kBlock) relabel_kernel(const int32_t* __restrict__ gid, int32_t* __restrict__ agg_src,
                                                          const int32_t* __restrict__ ec, const DedupMap map, int32_t l2) {
+  pdl_prologue();
   const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   const int32_t off = ec[0], E = ec[1];
   const int32_t p0 = (blockIdx.x * kBlock + threadIdx.x) * 4;
@@ -570,6 +579,7 @@ __global__ void __launch_bounds__(kBlock) relabel_kernel(const int32_t* __restri
 // O(batch) work; the map itself is O(N) like the reference's, but never memset.
 __global__ void __launch_bounds__(kBlock) pm_clear_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ nc,
                                                           uint32_t* pm, int32_t l2) {
+  pdl_prologue();
   const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   int32_t n = nc[LG_INTRABATCH_CON * 2 + 1];
   const int32_t seeds = nc[LG_INTRABATCH_CON * 3];
@@ -580,10 +590,21 @@ __global__ void __launch_bounds__(kBlock) pm_clear_kernel(const int32_t* __restr
   }
 }
 
+// Streaming release of a whole map: 16-byte stores of all-ones over `n16` uint4 words.  Used for the HASHED table
+// (32 MB per batch) and for small dense maps, where one pass over 4N bytes at store bandwidth beats the O(batch)
+// scatter of pm_clear_kernel (products: 9.8 MB vs ~0.9 M random 4-byte stores).  A kernel rather than a memset node
+// so that the chain stays kernel -> kernel (PDL).
+__global__ void __launch_bounds__(kBlock) map_fill_kernel(uint4* __restrict__ p, int64_t n16) {
+  pdl_prologue();
+  const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) p[i] = ones;
+}
+
 // HotnessMeasure (cache/cache_impl.cuh:190-198) + max_ids_ (cache/cache.cu:59-61)
 __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* __restrict__ ids,
                                                                  const int32_t* __restrict__ nc, u64* node_hot,
                                                                  int32_t* max_ids) {
+  pdl_prologue();
   const int32_t n = nc[LG_INTRABATCH_CON * 2 + 1];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int32_t cid = ids[i];
@@ -597,29 +618,28 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// Shared-memory carve-out of the sampler kernels (LG_CARVEOUT=<percent>, default -1 = the driver's choice).
-// An SM's unified L1/shared array is configured per resident kernel; the gather needs ~160 KB of shared memory per
-// SM, and an SM that holds even ONE CTA of a kernel configured for a small carve-out cannot take the gather's CTAs
-// until it has drained (one spinning warp per SM stretches the gather from 0.135 to 0.200 ms; with the spinner's
-// carve-out at 100 % the gather is unaffected).  Forcing 100 % on the sampler kernels was measured and REJECTED: their
-// L1 shrinks to ~28 KB, hop 2 slows from 0.100 to 0.137 ms, and the pipelined step gets worse (0.252 vs 0.227 ms) —
-// next to the real sampler the gather is slowed by something else than CTA placement (profiles/r01b_overlap.md).
-static int carveout_pct() {
-  static int v = [] {
-    const char* e = getenv("LG_CARVEOUT");
-    return e ? atoi(e) : -1;
+// Tuning knobs of the sampler chain (environment, read once; defaults are the measured best, profiles/r01d_waves.md):
+//   LG_SAMPLE_TILE   frontier entries per CTA of the long hops (32..256)
+//   LG_SAMPLE_MINB   6 = cap the sample kernel at 40 registers so that 6 CTAs fit an SM (one wave for 200 k entries)
+//   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8, 12 or 16)
+//   LG_RANK_MINB     6 = cap the rank kernel at 40 registers
+//   LG_PM_FILL_MB    dense position maps up to this size are released by a streaming fill instead of the O(batch) scatter
+// (A forced shared-memory carve-out on these kernels was measured and rejected: profiles/r01b_overlap.md.)
+struct SamplerTune {
+  int sample_tile, sample_minb, rank_items, rank_minb, pm_fill_mb;
+};
+static const SamplerTune& sampler_tune() {
+  static SamplerTune t = [] {
+    SamplerTune x{0, 0, 0, 0, 0};
+    if (const char* e = getenv("LG_SAMPLE_TILE")) x.sample_tile = atoi(e);
+    if (const char* e = getenv("LG_SAMPLE_MINB")) x.sample_minb = atoi(e);
+    if (const char* e = getenv("LG_RANK_ITEMS")) x.rank_items = atoi(e);
+    if (const char* e = getenv("LG_RANK_MINB")) x.rank_minb = atoi(e);
+    if (const char* e = getenv("LG_PM_FILL_MB")) x.pm_fill_mb = atoi(e);
+    return x;
   }();
-  return v;
+  return t;
 }
-#define LG_CARVEOUT(kernel)                                                                            \
-  do {                                                                                                 \
-    static bool done_ = false;                                                                         \
-    if (!done_) {                                                                                      \
-      done_ = true;                                                                                    \
-      if (carveout_pct() >= 0)                                                                         \
-        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct()); \
-    }                                                                                                  \
-  } while (0)
 
 extern "C" int64_t lg_num_ids(int32_t batch_size, const int32_t* fanout, int32_t n_hops) {
   int64_t tot = batch_size, per = batch_size;  // engine/server.cu:187-199
@@ -637,9 +657,15 @@ static int pick_tile_f(int64_t frontier_max) {
   if (frontier_max >= 64ll * kSMs) return 64;
   return 32;
 }
+static int pick_tile_f_tuned(int64_t frontier_max) {
+  const int t = pick_tile_f(frontier_max), o = sampler_tune().sample_tile;
+  return (t == 256 && (o == 32 || o == 64 || o == 128 || o == 256)) ? o : t;
+}
 static int pick_rank_items(int64_t edges_max) {
   // all tiles of a hop resident at once when possible (6 CTAs x 148 SMs): 8 edges per thread up to ~1.8 M edges
-  return (edges_max > 4ll * kBlock * kSMs * 5) ? 8 : 4;
+  if (edges_max <= 4ll * kBlock * kSMs * 5) return 4;
+  const int o = sampler_tune().rank_items;
+  return (o == 4 || o == 8 || o == 12 || o == 16) ? o : 8;
 }
 
 extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
@@ -667,7 +693,7 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_REQUIRE(s->num_ids < (1ll << 31), "lg_sampler_create: num_ids %lld does not fit int32", (long long)s->num_ids);
   int64_t smax = s->slots_per_hop[n_hops];
   if (smax < 2ll * max_batch) smax = 2ll * max_batch;  // head of gid[1] doubles as the e2e seed staging area
-  smax = (smax + kBlock * 8 - 1) / (kBlock * 8) * (kBlock * 8);  // whole rank tiles: vector loads never leave the buffer
+  smax = (smax + kBlock * 48 - 1) / (kBlock * 48) * (kBlock * 48);  // whole rank tiles (4, 8, 12 or 16 edges per thread): vector loads never leave the buffer
   for (int b = 0; b < 2; b++) {
     LG_CUDA(cudaMalloc(&s->gid[b], (size_t)smax * sizeof(int32_t)));
     LG_CUDA(cudaMemset(s->gid[b], 0, (size_t)smax * sizeof(int32_t)));
@@ -697,7 +723,7 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   bytes = (bytes + 255) & ~255ll;
   int64_t off_state[2][LG_MAX_HOPS], off_anchor[2][LG_MAX_HOPS];
   for (int h = 0; h < n_hops; h++) {
-    int tf = pick_tile_f(s->slots_per_hop[h]);
+    int tf = pick_tile_f_tuned(s->slots_per_hop[h]);
     s->sample_tile_f[h] = tf;
     s->sample_tiles[h] = (int32_t)((s->slots_per_hop[h] + tf - 1) / tf);
     s->rank_items[h] = pick_rank_items(s->slots_per_hop[h + 1]);
@@ -844,9 +870,11 @@ extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
 // the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
 static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
   if (!s->hashed) {  // HASHED: the table is re-initialised by the next lg_batch_generate instead
-    LG_CARVEOUT((pm_clear_kernel));
-    pm_clear_kernel<<<kSMs * 4, kBlock, 0, st>>>(b->ids, b->node_counter, s->pm, lg_l2_hints());
-    LG_LAUNCH_OK();
+    if (s->num_nodes * 4 <= (int64_t)sampler_tune().pm_fill_mb * (1ll << 20) && (s->num_nodes & 3) == 0)
+      LG_CUDA(lg_launch(map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->pm, s->num_nodes / 4));
+    else
+      LG_CUDA(lg_launch(pm_clear_kernel, kSMs * 4, kBlock, 0, st, (const int32_t*)b->ids,
+                        (const int32_t*)b->node_counter, s->pm, lg_l2_hints()));
   }
   s->pm_dirty = 0;
   return 0;
@@ -872,40 +900,59 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
     int rc = clear_position_map(s, st, &s->dirty_batch);
     if (rc) return rc;
   }
-  if (s->hashed)  // O(batch)-sized table, L2-resident: one streaming memset instead of an O(batch) random clear
-    LG_CUDA(cudaMemsetAsync(s->table, 0xFF, ((size_t)s->table_mask + 1) * sizeof(u64), st));
-  // reset of the per-batch scan state (tickets + tile aggregates); the position map needs no reset
-  // (the reference memsets an N/8-byte bitmap here, :151)
-  LG_CUDA(cudaMemsetAsync(s->small, 0, (size_t)s->small_bytes, st));
+  if (s->hashed)  // O(batch)-sized table, L2-resident: one streaming fill instead of an O(batch) random clear
+    LG_CUDA(lg_launch(map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->table, ((int64_t)s->table_mask + 1) / 2));
   long long done = (long long)batch_size * ((long long)counter + 1);
   int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
   if (size < 0) size = 0;
   int grid = size > 0 ? (size + kBlock - 1) / kBlock : 1;
+  // the kernel also zeroes the per-batch scan state (tickets + tile aggregates): enough threads for one pass
+  const int32_t small_words = (int32_t)(s->small_bytes / 8);
+  const int grid_small = (small_words + kBlock - 1) / kBlock;
+  if (grid < grid_small) grid = grid_small < 64 ? grid_small : 64;
   if (s->hashed) {
-    LG_CARVEOUT((batch_generate_kernel<true>));
-    batch_generate_kernel<true><<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
-                                                         b->labels, b->node_counter, b->edge_counter, map_of(s), lg_l2_hints());
-    LG_CARVEOUT((seed_local_kernel));
-    seed_local_kernel<<<grid, kBlock, 0, st>>>(b->ids, b->node_counter, s->seed_local, map_of(s), lg_l2_hints());
+    LG_CUDA(lg_launch(batch_generate_kernel<true>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
+                      s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
+                      small_words, lg_l2_hints()));
+    LG_CUDA(lg_launch(seed_local_kernel, grid, kBlock, 0, st, (const int32_t*)b->ids, (const int32_t*)b->node_counter,
+                      s->seed_local, map_of(s), lg_l2_hints()));
   } else {
-    LG_CARVEOUT((batch_generate_kernel<false>));
-    batch_generate_kernel<false><<<grid, kBlock, 0, st>>>(all_ids, all_labels, total_cap, size, counter, s->n_hops, b->ids,
-                                                          b->labels, b->node_counter, b->edge_counter, map_of(s), lg_l2_hints());
+    LG_CUDA(lg_launch(batch_generate_kernel<false>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
+                      s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
+                      small_words, lg_l2_hints()));
   }
-  LG_LAUNCH_OK();
   s->pm_dirty = 1;
   s->dirty_batch = *b;
   return 0;
 }
 
-template <int RNG, bool HASHED>
-static void launch_sample(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
+template <int RNG, bool HASHED, int MINB>
+static cudaError_t launch_sample_minb(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
   switch (tile_f) {
-    case 256: LG_CARVEOUT((sample_hop_kernel<256, RNG, HASHED>)); sample_hop_kernel<256, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
-    case 128: LG_CARVEOUT((sample_hop_kernel<128, RNG, HASHED>)); sample_hop_kernel<128, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
-    case 64: LG_CARVEOUT((sample_hop_kernel<64, RNG, HASHED>)); sample_hop_kernel<64, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
-    default: LG_CARVEOUT((sample_hop_kernel<32, RNG, HASHED>)); sample_hop_kernel<32, RNG, HASHED><<<grid, kBlock, 0, st>>>(a); break;
+    case 256: return lg_launch(sample_hop_kernel<256, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
+    case 128: return lg_launch(sample_hop_kernel<128, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
+    case 64: return lg_launch(sample_hop_kernel<64, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
+    default: return lg_launch(sample_hop_kernel<32, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
   }
+}
+template <int RNG, bool HASHED>
+static cudaError_t launch_sample(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
+  if (sampler_tune().sample_minb == 6) return launch_sample_minb<RNG, HASHED, 6>(tile_f, grid, st, a);
+  return launch_sample_minb<RNG, HASHED, 0>(tile_f, grid, st, a);
+}
+template <bool HASHED, int MINB>
+static cudaError_t launch_rank_minb(int items, int grid, cudaStream_t st, const RankArgs& r) {
+  switch (items) {
+    case 16: return lg_launch(rank_kernel<16, HASHED, MINB>, grid, kBlock, 0, st, r);
+    case 12: return lg_launch(rank_kernel<12, HASHED, MINB>, grid, kBlock, 0, st, r);
+    case 8: return lg_launch(rank_kernel<8, HASHED, MINB>, grid, kBlock, 0, st, r);
+    default: return lg_launch(rank_kernel<4, HASHED, MINB>, grid, kBlock, 0, st, r);
+  }
+}
+template <bool HASHED>
+static cudaError_t launch_rank(int items, int grid, cudaStream_t st, const RankArgs& r) {
+  if (sampler_tune().rank_minb == 6) return launch_rank_minb<HASHED, 6>(items, grid, st, r);
+  return launch_rank_minb<HASHED, 0>(items, grid, st, r);
 }
 
 // one hop: sample + rank (+ the hop's own relabel pass unless the caller folds it into the next hop's sample kernel)
@@ -943,13 +990,12 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   a.l2 = lg_l2_hints();
   a.trace = s->trace;
   if (rng_kind == LG_RNG_MINSTD) {
-    if (s->hashed) launch_sample<LG_RNG_MINSTD, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
-    else launch_sample<LG_RNG_MINSTD, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_MINSTD, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_MINSTD, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
   } else {
-    if (s->hashed) launch_sample<LG_RNG_PHILOX, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
-    else launch_sample<LG_RNG_PHILOX, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a);
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_PHILOX, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
   }
-  LG_LAUNCH_OK();
   RankArgs r;
   r.gid = s->gid[h & 1];
   r.ids = b->ids;
@@ -965,24 +1011,16 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   r.l2 = lg_l2_hints();
   r.status = s->status;
   r.trace = s->trace;
-  if (s->hashed) {
-    if (s->rank_items[h] == 8) { LG_CARVEOUT((rank_kernel<8, true>)); rank_kernel<8, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
-    else { LG_CARVEOUT((rank_kernel<4, true>)); rank_kernel<4, true><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
-  } else {
-    if (s->rank_items[h] == 8) { LG_CARVEOUT((rank_kernel<8, false>)); rank_kernel<8, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
-    else { LG_CARVEOUT((rank_kernel<4, false>)); rank_kernel<4, false><<<s->rank_tiles[h], kBlock, 0, st>>>(r); }
-  }
-  LG_LAUNCH_OK();
+  if (s->hashed) LG_CUDA(launch_rank<true>(s->rank_items[h], s->rank_tiles[h], st, r));
+  else LG_CUDA(launch_rank<false>(s->rank_items[h], s->rank_tiles[h], st, r));
   if (relabel_own) {
     const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
-    if (s->hashed) {
-      LG_CARVEOUT((relabel_kernel<true>));
-      relabel_kernel<true><<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, map_of(s), lg_l2_hints());
-    } else {
-      LG_CARVEOUT((relabel_kernel<false>));
-      relabel_kernel<false><<<(int)grid, kBlock, 0, st>>>(s->gid[h & 1], b->agg_src, b->edge_counter, map_of(s), lg_l2_hints());
-    }
-    LG_LAUNCH_OK();
+    if (s->hashed)
+      LG_CUDA(lg_launch(relabel_kernel<true>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
+                        (const int32_t*)b->edge_counter, map_of(s), lg_l2_hints()));
+    else
+      LG_CUDA(lg_launch(relabel_kernel<false>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
+                        (const int32_t*)b->edge_counter, map_of(s), lg_l2_hints()));
   }
   return 0;
 }
@@ -1009,9 +1047,8 @@ extern "C" int lg_io_complete(lg_sampler* s, lg_stream_t stream_, int32_t mode, 
   LG_REQUIRE(s && b, "lg_io_complete: null argument");
   cudaStream_t st = (cudaStream_t)stream_;
   if (mode == LG_TRAINMODE && node_hotness) {  // :558
-    LG_CARVEOUT((hotness_measure_kernel));
-    hotness_measure_kernel<<<kSMs * 2, kBlock, 0, st>>>(b->ids, b->node_counter, (u64*)node_hotness, max_ids);
-    LG_LAUNCH_OK();
+    LG_CUDA(lg_launch(hotness_measure_kernel, kSMs * 2, kBlock, 0, st, (const int32_t*)b->ids,
+                      (const int32_t*)b->node_counter, (u64*)node_hotness, max_ids));
   }
   // ClearPosMap: the reference clears in train mode only (its bitmap makes stale entries harmless in the
   // other modes); the position map is the only dedup state here, so it is released in every mode
