@@ -9,12 +9,17 @@
 
 int lg_set_error(const char* fmt, ...);
 int lg_l2_hints();  // LG_L2_HINTS bitmask (see the L2 eviction-priority helpers below)
-int lg_pdl();       // LG_PDL (default 1): launch the per-batch kernel chain with programmatic stream serialization
+int lg_pdl();       // LG_PDL bitmask (default 1): bit 0 launch the per-batch kernel chain with programmatic stream
+                    // serialization; bit 1 except the position-map release (first kernel after the gather is forked);
+                    // bit 2 except batch_generate (first kernel of a batch)
+int lg_chain_carveout();  // LG_CARVEOUT: preferred shared-memory carve-out (%) of the sampler-chain kernels, -1 = driver's choice
+void lg_apply_carveout(const void* kernel);
 
 // kernel launch of the per-batch chain: cudaLaunchKernelEx, with the PDL attribute when enabled
 template <typename... KArgs, typename... Args>
-static inline cudaError_t lg_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
-                                    Args... args) {
+static inline cudaError_t lg_launch_opt(bool allow_pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem,
+                                        cudaStream_t st, Args... args) {
+  if (lg_chain_carveout() >= 0) lg_apply_carveout((const void*)kernel);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -22,13 +27,18 @@ static inline cudaError_t lg_launch(void (*kernel)(KArgs...), int grid, int bloc
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  if (lg_pdl()) {
+  if (allow_pdl && (lg_pdl() & 1)) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lg_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                                    Args... args) {
+  return lg_launch_opt(true, kernel, grid, block, smem, st, args...);
 }
 
 #define LG_CUDA(expr)                                                                       \
@@ -95,15 +105,20 @@ __device__ __forceinline__ int32_t pick_neighbor(uint32_t slot, int32_t deg, uin
   return (int32_t)__umulhi(r, (uint32_t)deg);
 }
 
-// ---- programmatic dependent launch (PDL).  Every kernel of the per-batch chain starts with pdl_prologue(): it lets the
-//      NEXT kernel of the stream become resident right away (griddepcontrol.launch_dependents) and then waits until
-//      every kernel before it has completed and flushed (griddepcontrol.wait).  The successor is only dispatched once
-//      ALL CTAs of this grid have started, and it blocks in its own wait until this grid is done, so the chain keeps
-//      stream order for memory; what disappears is the launch latency between dependent kernels.  Without the launch
-//      attribute (LG_PDL=0, or a kernel launched with <<<>>>) both instructions are no-ops. ----
+// ---- programmatic dependent launch (PDL).  Every kernel of the per-batch chain starts with pdl_prologue():
+//      griddepcontrol.wait blocks until every kernel before it in the stream has completed and flushed; then the
+//      NEXT kernel of the stream is allowed to become resident (griddepcontrol.launch_dependents) — it blocks in its
+//      own wait until this grid is done, so stream order holds for memory and only the launch latency between
+//      dependent kernels disappears.  The gpu-scope fence after the wait is NOT optional: it invalidates this SM's L1
+//      (CCTL.IVALL).  A PDL grid is dispatched — and the launch-time L1 invalidation happens — while its parent still
+//      runs; CTAs of the parent on the same SM keep filling L1 with sectors (counters, position-map words) that other
+//      CTAs of the parent rewrite later, and a plain load after the wait would hit those stale sectors (seen on the
+//      GPU: hotness_measure_kernel read the previous hop's nc[7]).  Without the launch attribute (LG_PDL=0, or a
+//      kernel launched with <<<>>>) wait and launch_dependents are no-ops. ----
 __device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  __threadfence();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---- relaxed gpu-scope 64-bit accesses (cross-CTA flags and dedup-table words) ----

@@ -335,16 +335,17 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
 // tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {4,8}, LG_TMA_STAGES {3,4,6},
 // LG_LDG_CTAS resident CTAs per SM assumed when sizing the LDG grid
 struct Tune {
-  int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows, carveout;
+  int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows, carveout, smem_kb;
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 3, 8, 4, 32, -1};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
+    Tune x{8, 3, 8, 4, 32, -1, 220};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
     if (const char* e = getenv("LG_LDG_CTAS")) x.ldg_ctas = atoi(e);
-    if (const char* e = getenv("LG_TMA_CTAS")) x.tma_ctas = atoi(e);
+    if (const char* e = getenv("LG_TMA_CTAS")) x.tma_ctas = atoi(e);  // cap in units of 32-row tiles
     if (const char* e = getenv("LG_TMA_ROWS")) x.tma_rows = atoi(e);
+    if (const char* e = getenv("LG_GATHER_SMEM_KB")) x.smem_kb = atoi(e);  // shared memory the TMA gather may hold per SM (the rest stays L1 for co-resident sampler CTAs)
     if (const char* e = getenv("LG_GATHER_CARVEOUT")) x.carveout = atoi(e);  // preferred smem carve-out (%) of the TMA gather  // rows per tile of a single-warp CTA: 8, 16 or 32  // cap on resident gather CTAs per SM (smem left for the sampler)
     return x;
   }();
@@ -355,13 +356,18 @@ template <int STAGES, int ROWS>
 int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
   const size_t smem = (size_t)a.cache.dim * 4 * ROWS * STAGES;
   LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (tune().carveout >= 0)
-    LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES, ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().carveout));
-  int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+  int ctas_per_sm = (int)(((size_t)tune().smem_kb * 1024) / (smem + 1024));
   const int cap = tune().tma_ctas * (32 / ROWS);  // the cap is stated for 32-row tiles: same bytes in flight per SM
   if (ctas_per_sm > cap) ctas_per_sm = cap;
   if (ctas_per_sm > 24) ctas_per_sm = 24;  // leave CTA slots (32 per SM) to the sampler
   if (ctas_per_sm < 1) ctas_per_sm = 1;
+  {  // carve-out: exactly what the resident CTAs need (the SM rounds up to its next configuration), or LG_GATHER_CARVEOUT
+    int pct = tune().carveout;
+    if (pct < 0 && tune().smem_kb != 220) pct = (int)((100 * (size_t)ctas_per_sm * (smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    if (pct >= 0)
+      LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES, ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   int64_t tiles = (max_rows + ROWS - 1) / ROWS;
   int64_t grid = (int64_t)kSMs * ctas_per_sm;
   if (tiles < grid) grid = tiles > 0 ? tiles : 1;

@@ -29,6 +29,23 @@ int lg_pdl() {  // see common.cuh; read once
   return v;
 }
 
+int lg_chain_carveout() {  // see common.cuh; read once
+  static int v = [] {
+    const char* e = getenv("LG_CARVEOUT");
+    return e ? atoi(e) : -1;
+  }();
+  return v;
+}
+void lg_apply_carveout(const void* kernel) {  // once per kernel
+  static std::mutex mu;
+  static std::vector<const void*> done;
+  std::lock_guard<std::mutex> g(mu);
+  for (const void* k : done)
+    if (k == kernel) return;
+  done.push_back(kernel);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, lg_chain_carveout());
+}
+
 int lg_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -762,6 +762,7 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   for (int h = 0; h <= LG_MAX_HOPS; h++) LG_CUDA(cudaEventCreateWithFlags(&s->ev_fork[h], cudaEventDisableTiming));
   LG_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  LG_CUDA(cudaEventCreateWithFlags(&s->ev_clear, cudaEventDisableTiming));
   s->overlap = 1;
   s->fuse_gathers = 1;
   *out = s;
@@ -783,6 +784,7 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaStreamDestroy(s->side);
   for (int h = 0; h <= LG_MAX_HOPS; h++) cudaEventDestroy(s->ev_fork[h]);
   cudaEventDestroy(s->ev_join);
+  cudaEventDestroy(s->ev_clear);
   for (int i = 0; i < s->n_done; i++) cudaEventDestroy(s->done[i].ev);
   delete s;
   return 0;
@@ -871,10 +873,14 @@ extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
 static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
   if (!s->hashed) {  // HASHED: the table is re-initialised by the next lg_batch_generate instead
     if (s->num_nodes * 4 <= (int64_t)sampler_tune().pm_fill_mb * (1ll << 20) && (s->num_nodes & 3) == 0)
-      LG_CUDA(lg_launch(map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->pm, s->num_nodes / 4));
+      LG_CUDA(lg_launch_opt(!(lg_pdl() & 2), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->pm, s->num_nodes / 4));
     else
-      LG_CUDA(lg_launch(pm_clear_kernel, kSMs * 4, kBlock, 0, st, (const int32_t*)b->ids,
+      LG_CUDA(lg_launch_opt(!(lg_pdl() & 2), pm_clear_kernel, kSMs * 4, kBlock, 0, st, (const int32_t*)b->ids,
                         (const int32_t*)b->node_counter, s->pm, lg_l2_hints()));
+    // the next batch's inserts must not overtake this release when the host enqueues them on another stream
+    LG_CUDA(cudaEventRecord(s->ev_clear, st));
+    s->clear_stream = st;
+    s->clear_recorded = 1;
   }
   s->pm_dirty = 0;
   return 0;
@@ -900,8 +906,9 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
     int rc = clear_position_map(s, st, &s->dirty_batch);
     if (rc) return rc;
   }
+  if (s->clear_recorded && s->clear_stream != st) LG_CUDA(cudaStreamWaitEvent(st, s->ev_clear, 0));
   if (s->hashed)  // O(batch)-sized table, L2-resident: one streaming fill instead of an O(batch) random clear
-    LG_CUDA(lg_launch(map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->table, ((int64_t)s->table_mask + 1) / 2));
+    LG_CUDA(lg_launch_opt(!(lg_pdl() & 4), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->table, ((int64_t)s->table_mask + 1) / 2));
   long long done = (long long)batch_size * ((long long)counter + 1);
   int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
   if (size < 0) size = 0;
@@ -911,13 +918,13 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   const int grid_small = (small_words + kBlock - 1) / kBlock;
   if (grid < grid_small) grid = grid_small < 64 ? grid_small : 64;
   if (s->hashed) {
-    LG_CUDA(lg_launch(batch_generate_kernel<true>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
+    LG_CUDA(lg_launch_opt(!(lg_pdl() & 4), batch_generate_kernel<true>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
                       s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
                       small_words, lg_l2_hints()));
     LG_CUDA(lg_launch(seed_local_kernel, grid, kBlock, 0, st, (const int32_t*)b->ids, (const int32_t*)b->node_counter,
                       s->seed_local, map_of(s), lg_l2_hints()));
   } else {
-    LG_CUDA(lg_launch(batch_generate_kernel<false>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
+    LG_CUDA(lg_launch_opt(!(lg_pdl() & 4), batch_generate_kernel<false>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
                       s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
                       small_words, lg_l2_hints()));
   }

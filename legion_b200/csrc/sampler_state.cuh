@@ -26,6 +26,9 @@ struct lg_sampler {
   int32_t hashed;        // 0 dense pm, 1 hashed table (chosen at create time by the size of the graph)
   int32_t pm_dirty;      // a batch was generated and its words not yet released (lg_io_complete)
   lg_batch dirty_batch;
+  cudaEvent_t ev_clear;        // recorded after the last release of the position map (lg_io_complete may run on
+  cudaStream_t clear_stream;   // another stream than the next lg_batch_generate: engine/server.cu puts it on stream 2)
+  int32_t clear_recorded;
   int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)
   uint8_t* small;        // memset-per-batch region: HopState[hops] + chained-scan tile states
   int64_t small_bytes;

@@ -10,7 +10,7 @@ j=json.loads(line[-1]);r=j['roofline'];print('$2', round(j['value']/1e6,2),'M se
 i=0
 while read -r line; do
   i=$((i+1))
-  env $line timeout 600 python bench.py --no-cpu-baseline --no-server-e2e ${BENCH_ARGS:-} > gpurun_out/bench_q_$i.json 2> gpurun_out/bench_q_$i.err || tail -5 gpurun_out/bench_q_$i.err
+  env $line timeout ${BENCH_TIMEOUT:-400} python bench.py --no-cpu-baseline --no-server-e2e ${BENCH_ARGS:-} > gpurun_out/bench_q_$i.json 2> gpurun_out/bench_q_$i.err || tail -5 gpurun_out/bench_q_$i.err
   show gpurun_out/bench_q_$i.json "$line"
 done <<EOL
 ${CONFIGS}

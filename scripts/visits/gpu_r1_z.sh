@@ -6,4 +6,4 @@ CONFIGS='LG_TMA_ROWS=32
 LG_TMA_ROWS=16
 LG_TMA_ROWS=8
 LG_TMA_ROWS=8 LG_TMA_CTAS=5
-LG_TMA_ROWS=8 LG_TMA_STAGES=4' bash scripts/gpu_r1_q.sh
+LG_TMA_ROWS=8 LG_TMA_STAGES=4' bash scripts/gpu_ab.sh
