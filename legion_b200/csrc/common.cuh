@@ -9,9 +9,9 @@
 
 int lg_set_error(const char* fmt, ...);
 int lg_l2_hints();  // LG_L2_HINTS bitmask (see the L2 eviction-priority helpers below)
-int lg_pdl();       // LG_PDL bitmask (default 1): bit 0 launch the per-batch kernel chain with programmatic stream
-                    // serialization; bit 1 except the position-map release (first kernel after the gather is forked);
-                    // bit 2 except batch_generate (first kernel of a batch)
+int lg_pdl();  // LG_PDL: -1 unset (per-handle default: on for the dense position map, off for the hashed one — measured),
+               // else a bitmask: bit 0 launch the per-batch kernel chain with programmatic stream serialization;
+               // bit 1 except the position-map release; bit 2 except batch_generate
 int lg_chain_carveout();  // LG_CARVEOUT: preferred shared-memory carve-out (%) of the sampler-chain kernels, -1 = driver's choice
 void lg_apply_carveout(const void* kernel);
 
@@ -27,7 +27,7 @@ static inline cudaError_t lg_launch_opt(bool allow_pdl, void (*kernel)(KArgs...)
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  if (allow_pdl && (lg_pdl() & 1)) {
+  if (allow_pdl) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
@@ -35,12 +35,6 @@ static inline cudaError_t lg_launch_opt(bool allow_pdl, void (*kernel)(KArgs...)
   }
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
-template <typename... KArgs, typename... Args>
-static inline cudaError_t lg_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
-                                    Args... args) {
-  return lg_launch_opt(true, kernel, grid, block, smem, st, args...);
-}
-
 #define LG_CUDA(expr)                                                                       \
   do {                                                                                      \
     cudaError_t e_ = (expr);                                                                \

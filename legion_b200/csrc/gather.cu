@@ -332,21 +332,27 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   }
 }
 
-// tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {4,8}, LG_TMA_STAGES {3,4,6},
-// LG_LDG_CTAS resident CTAs per SM assumed when sizing the LDG grid
+// tuning knobs (environment, read once): LG_LDG_R rows in flight per warp {4,8}, LG_LDG_CTAS resident CTAs per SM assumed
+// when sizing the LDG grid; TMA mover: LG_TMA_ROWS rows per tile {8,16,32}, LG_TMA_STAGES {3,4,6}, LG_GATHER_SMEM_KB shared
+// memory the gather may hold per SM, LG_TMA_CTAS cap on CTAs per SM in units of 32-row tiles, LG_GATHER_CARVEOUT (%).
+// Defaults (profiles/r01d_gather_footprint.md): 8-row tiles, 3 stages, 130 KB per SM.  The gather runs next to the
+// sampler's kernels, and whatever shared memory it configures on an SM is taken from the L1 of the sampler CTAs on that
+// SM: with 32-row tiles of 512-byte rows (4 CTAs x 48 KB = the whole array) the hashed sampler slowed down by 40 % while
+// co-resident.  8-row tiles on 10-12 single-warp CTAs keep as many bytes in flight with 130 KB (alone: 0.81 of the HBM peak
+// instead of 0.85 at D=128, unchanged at D=100) and leave 124 KB of L1: UK-Union shape 16.4 -> 18.9 M seeds/s.
 struct Tune {
   int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows, carveout, smem_kb;
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 3, 8, 4, 32, -1, 220};  // LDG: R=8 rows per warp; TMA: 3 stages (most CTAs per SM) — profiles/r01_gather_sweep_v3.txt
+    Tune x{8, 3, 8, 8, 8, -1, 130};  // LDG: R=8 rows per warp (profiles/r01_gather_sweep_v3.txt)
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
     if (const char* e = getenv("LG_LDG_CTAS")) x.ldg_ctas = atoi(e);
     if (const char* e = getenv("LG_TMA_CTAS")) x.tma_ctas = atoi(e);  // cap in units of 32-row tiles
     if (const char* e = getenv("LG_TMA_ROWS")) x.tma_rows = atoi(e);
-    if (const char* e = getenv("LG_GATHER_SMEM_KB")) x.smem_kb = atoi(e);  // shared memory the TMA gather may hold per SM (the rest stays L1 for co-resident sampler CTAs)
-    if (const char* e = getenv("LG_GATHER_CARVEOUT")) x.carveout = atoi(e);  // preferred smem carve-out (%) of the TMA gather  // rows per tile of a single-warp CTA: 8, 16 or 32  // cap on resident gather CTAs per SM (smem left for the sampler)
+    if (const char* e = getenv("LG_GATHER_SMEM_KB")) x.smem_kb = atoi(e);
+    if (const char* e = getenv("LG_GATHER_CARVEOUT")) x.carveout = atoi(e);
     return x;
   }();
   return t;
@@ -363,7 +369,7 @@ int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   {  // carve-out: exactly what the resident CTAs need (the SM rounds up to its next configuration), or LG_GATHER_CARVEOUT
     int pct = tune().carveout;
-    if (pct < 0 && tune().smem_kb != 220) pct = (int)((100 * (size_t)ctas_per_sm * (smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+    if (pct < 0) pct = (int)((100 * (size_t)ctas_per_sm * (smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
     if (pct > 100) pct = 100;
     if (pct >= 0)
       LG_CUDA(cudaFuncSetAttribute(gather_tma_kernel<STAGES, ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));

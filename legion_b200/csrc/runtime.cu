@@ -24,7 +24,7 @@ int lg_l2_hints() {  // see common.cuh; read once
 int lg_pdl() {  // see common.cuh; read once
   static int v = [] {
     const char* e = getenv("LG_PDL");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : -1;
   }();
   return v;
 }

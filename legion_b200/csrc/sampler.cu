@@ -40,7 +40,6 @@ constexpr int kBlock = 256;
 constexpr int kSlotUnroll = 5;              // neighbour reads in flight per thread in sample_hop_kernel
 constexpr bool kHashPrecheck = false;      // L1-cached pre-read before the atomic: +3% on a hub-heavy 2.4 M-vertex graph, -5% at UK-Union scale (the regime HASHED is for)
 constexpr int kSlotUnrollHashed = 5;        // HASHED: 10 in flight was measured slower (registers): 0.195 vs 0.174 ms for hop 2 at UK-Union scale
-constexpr int kAnchor = 1024;               // chained scan: every kAnchor-th tile also publishes its inclusive prefix
 
 // optional per-tile phase timestamps (diagnostics only: lg_debug_set_trace; nullptr in production)
 constexpr int kTraceTiles = 2048, kTracePhases = 8;
@@ -118,38 +117,53 @@ __device__ __forceinline__ uint32_t map_lookup(const DedupMap& m, uint32_t v, u6
 }
 
 // ------------------------------------------------------------------------------------------
-// Exclusive prefix of a tile's aggregate over all earlier tiles, computed by the WHOLE block.
-// Every tile posts (1<<32 | aggregate) once; a tile sums its predecessors' aggregates directly — all loads of a
-// round are in flight together, so the cost is one L2 round trip instead of a chain of dependent look-back
-// windows (measured: 7-10 us per kernel with the classic 32-wide look-back when ~800 tiles start together).
-// To bound the reads for long kernels, tiles (kAnchor*m - 1) also publish their inclusive prefix; a tile sums
-// only the aggregates back to the last anchor boundary and adds that prefix.  Tiles are claimed through an
-// atomic ticket, so every predecessor is already running: the spins cannot deadlock.
-// state: [n_tiles] aggregates followed by [n_tiles / kAnchor + 1] anchor prefixes, zeroed per batch.
+// Exclusive prefix of a tile's aggregate over all earlier tiles, computed by the WHOLE block in one L2 round trip.
+// Two levels: a tile posts (1<<32 | aggregate) into its own word AND adds the same packed value to the word of its group
+// of kGroup consecutive tiles (count in the high half, sum in the low half: a group is complete when the count reaches
+// kGroup).  A tile then sums the words of the complete groups before its own (one load per group) and the words of the
+// earlier tiles of its own group (< kGroup loads) — all loads in flight together.  Group words sit on their own 128-byte
+// lines.  The first version summed every predecessor's word directly: with one wave of ~800 tiles that is ~300 k polls on
+// ~50 cache lines, and the lines of the lowest tiles were served for 8 us (p50) to 27 us (max) per kernel
+// (profiles/r01d_sampler_chain.md).  Tiles are claimed through an atomic ticket, so every predecessor is already
+// running: the spins cannot deadlock.
+// state: [n_tiles] tile words; groups: [n_tiles / kGroup + 1] x kGroupStride words; both zeroed per batch.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int32_t block_exclusive_prefix(u64* state, u64* anchors, int tile, int32_t aggregate,
+constexpr int kGroup = 32;
+constexpr int kGroupStride = 16;  // u64 words per group word: one 128-byte line each
+__device__ __forceinline__ void red_add_u64(u64* p, u64 v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int32_t block_exclusive_prefix(u64* state, u64* groups, int tile, int32_t aggregate,
                                                           int32_t* s_red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) st_relaxed(state + tile, (1ull << 32) | (uint32_t)aggregate);
-  const int a0 = (tile / kAnchor) * kAnchor;  // first tile whose aggregate we add
+  const int g = tile / kGroup, r = tile - g * kGroup;
+  if (tid == 0) {
+    const u64 word = (1ull << 32) | (uint32_t)aggregate;
+    st_relaxed(state + tile, word);
+    red_add_u64(groups + (size_t)g * kGroupStride, word);
+  }
   int32_t sum = 0;
-  if (a0 > 0 && tid == 0) {
-    u64 s = ld_relaxed(anchors + a0 / kAnchor);
-    while ((s >> 32) == 0ull) s = ld_relaxed(anchors + a0 / kAnchor);
+  // earlier tiles of the own group: threads of the last warp (so that the group loads below start on warp 0)
+  if (warp == kBlock / 32 - 1 && lane < r) {
+    const u64* p = state + g * kGroup + lane;
+    u64 s = ld_relaxed(p);
+    while ((s >> 32) == 0ull) {
+      __nanosleep(40);
+      s = ld_relaxed(p);
+    }
     sum = (int32_t)(uint32_t)s;
   }
-  for (int hi = tile - 1; hi >= a0; hi -= kBlock * 4) {
-    u64 s[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int idx = hi - tid - j * kBlock;
-      s[j] = (idx >= a0) ? ld_relaxed(state + idx) : (1ull << 32);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int idx = hi - tid - j * kBlock;
-      while ((s[j] >> 32) == 0ull) s[j] = ld_relaxed(state + idx);
-      sum += (int32_t)(uint32_t)s[j];
+  // complete groups before the own one
+  for (int j0 = 0; j0 < g; j0 += kBlock - 32) {
+    const int j = j0 + tid;
+    if (tid < kBlock - 32 && j < g) {
+      const u64* p = groups + (size_t)j * kGroupStride;
+      u64 s = ld_relaxed(p);
+      while ((s >> 32) != (u64)kGroup) {
+        __nanosleep(40);
+        s = ld_relaxed(p);
+      }
+      sum += (int32_t)(uint32_t)s;
     }
   }
   sum = warp_sum(sum);
@@ -158,8 +172,6 @@ __device__ __forceinline__ int32_t block_exclusive_prefix(u64* state, u64* ancho
   int32_t excl = 0;
 #pragma unroll
   for (int w = 0; w < kBlock / 32; w++) excl += s_red[w];
-  if (tid == 0 && ((tile + 1) % kAnchor) == 0)
-    st_relaxed(anchors + (tile + 1) / kAnchor, (1ull << 32) | (uint32_t)(excl + aggregate));
   __syncthreads();  // s_red may be reused by the caller
   return excl;
 }
@@ -239,7 +251,11 @@ struct SampleArgs {
   lg_topology topo;
   const int32_t* frontier_prev;  // hop > 1: global ids of the previous hop's sampled sources
   const int32_t* seed_local;     // HASHED: batch-local ids of the seeds (seed_local_kernel)
+  const u64* row_in;             // hop > 1: row descriptors of the frontier written by the previous hop (or null)
+  const int32_t* deg_in;
   int32_t* gid_out;              // this hop's sampled sources (global ids), hop-relative positions
+  u64* row_out;                  // PRODUCE: row descriptor (part << 56 | first edge) and degree of every sampled
+  int32_t* deg_out;              //          source = the next hop's frontier, so that hop starts without a lookup
   int32_t* ids;
   int32_t* agg_src;
   int32_t* agg_dst;
@@ -259,7 +275,19 @@ struct SampleArgs {
   u64* trace;
 };
 
-template <int TILE_F, int RNG, bool HASHED, int MINB>
+constexpr u64 kRowMask = (1ull << 56) - 1;
+
+// Row of vertex v: (part, first edge, degree) through the topology directory (FindTopo, cache/cache.cu:217-225)
+__device__ __forceinline__ void row_locate(const lg_topology& t, int32_t v, int32_t loc, int* part, long long* row) {
+  *part = t.n_parts;
+  *row = v;
+  if (loc >= 0) {
+    *part = loc / t.shard_rows;
+    *row = loc - *part * t.shard_rows;
+  }
+}
+
+template <int TILE_F, int RNG, bool HASHED, int MINB, bool PRODUCE>
 __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleArgs a) {
   static_assert(TILE_F <= kBlock, "one thread per frontier entry of the tile");
   __shared__ long long s_start[TILE_F];
@@ -292,35 +320,39 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
   const int32_t c = a.fanout;
   const int32_t i0 = tile * TILE_F;
 
-  // 1. row lookup for the tile's frontier entries
-  int32_t cnt = 0;
+  // 1. rows of the tile's frontier entries.  For hop > 1 the previous hop's sample kernel already looked them up
+  //    (row_in/deg_in, written next to gid_out): this phase is then two coalesced loads, and the chained prefix below —
+  //    which every later tile waits for — no longer sits behind a tail of dependent random reads.
+  int32_t cnt = 0, fl = 0;
+  bool live = false;
   if (tid < TILE_F) {
-    int32_t i = i0 + tid;
-    int32_t deg = 0, fl = 0;
+    const int32_t i = i0 + tid;
+    int32_t deg = 0;
     long long start = 0;
     const int32_t* ind = a.topo.indices[a.topo.n_parts];
     if (i < F) {
-      int32_t v = first_hop ? a.ids[i] : a.frontier_prev[i];
+      const int32_t v = first_hop ? a.ids[i] : a.frontier_prev[i];
       if (v >= 0) {
-        // batch-local index of the frontier vertex (position_map, :291-294): final since the previous op
-        if (HASHED) {  // never from the table while this launch inserts (see seed_local_kernel)
+        live = true;
+        // batch-local index of the frontier vertex (position_map, :291-294): final since the previous op.  The load
+        // is issued here and consumed after the prefix (s_flocal).
+        if (HASHED)  // never from the table while this launch inserts (see seed_local_kernel)
           fl = first_hop ? a.seed_local[i] : a.agg_src[prev_edge_off + i];
-        } else {
+        else
           fl = (int32_t)map_lookup<false>(a.map, (uint32_t)v, keep);
-          if (a.relabel_prev) a.agg_src[prev_edge_off + i] = fl;  // construct_graph of the previous hop, fused
+        int part;
+        if (a.row_in) {
+          const u64 r = a.row_in[i];
+          part = (int)(r >> 56);
+          start = (long long)(r & kRowMask);
+          deg = a.deg_in[i];
+        } else {
+          long long row;
+          row_locate(a.topo, v, a.topo.directory ? ld_nc_s32_hint(a.topo.directory + v, keep) : -1, &part, &row);
+          const int64_t* ip = a.topo.indptr[part];
+          start = ld_nc_s64_hint(ip + row, keep);
+          deg = (int32_t)(ld_nc_s64_hint(ip + row + 1, keep) - start);  // :226 (int32 col_size)
         }
-        int part = a.topo.n_parts;
-        long long row = v;
-        if (a.topo.directory) {
-          int32_t loc = ld_nc_s32_hint(a.topo.directory + v, keep);
-          if (loc >= 0) {
-            part = loc / a.topo.shard_rows;
-            row = loc - part * a.topo.shard_rows;
-          }
-        }
-        const int64_t* ip = a.topo.indptr[part];
-        start = ld_nc_s64_hint(ip + row, keep);
-        deg = (int32_t)(ld_nc_s64_hint(ip + row + 1, keep) - start);  // :226 (int32 col_size)
         ind = a.topo.indices[part];
         cnt = deg < c ? deg : c;
         if (cnt < 0) cnt = 0;
@@ -330,7 +362,6 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
     s_start[tid] = start;
     s_deg[tid] = deg;
     s_cnt[tid] = cnt;
-    s_flocal[tid] = fl;
     s_indices[tid] = ind;
   }
   if (tid == 0) trace_mark(a.trace, tslot, tile, 1);
@@ -341,6 +372,11 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
   if (tid < TILE_F) s_off[tid] = off;
   const int32_t base = block_exclusive_prefix(a.tile_state, a.anchors, tile, total, s_red);
   if (tid == 0 && tile == n_tiles - 1) a.ec[2] = base + total;  // E_h (:264)
+  if (tid < TILE_F) {
+    s_flocal[tid] = fl;
+    if (!HASHED && a.relabel_prev && live) a.agg_src[prev_edge_off + i0 + tid] = fl;  // construct_graph of the previous hop, fused
+  }
+  __syncthreads();
   if (tid == 0) trace_mark(a.trace, tslot, tile, 2);
 
   // 4. one thread per slot: pick, emit, min-insert into the position map.  U independent neighbour
@@ -427,6 +463,31 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
         }
       }
     }
+    if (PRODUCE) {  // the sampled sources are the next hop's frontier: look their rows up now, U at a time
+      int32_t loc[U];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        loc[u] = (p[u] >= 0 && a.topo.directory) ? ld_nc_s32_hint(a.topo.directory + w[u], keep) : -1;
+      long long e0[U], e1[U];
+      int part[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (p[u] >= 0) {
+          long long row;
+          row_locate(a.topo, w[u], loc[u], &part[u], &row);
+          const int64_t* ip = a.topo.indptr[part[u]];
+          e0[u] = ld_nc_s64_hint(ip + row, keep);
+          e1[u] = ld_nc_s64_hint(ip + row + 1, keep);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (p[u] >= 0) {
+          a.row_out[p[u]] = ((u64)part[u] << 56) | (u64)e0[u];
+          a.deg_out[p[u]] = (int32_t)(e1[u] - e0[u]);
+        }
+      }
+    }
   }
   if (a.trace) {
     if (tid == 0) trace_mark(a.trace, tslot, tile, 3);  // thread 0 done
@@ -455,8 +516,8 @@ struct RankArgs {
   u64* trace;
 };
 
-template <int ITEMS, bool HASHED, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) rank_kernel(const RankArgs a) {
+template <int ITEMS, bool HASHED>
+__global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
   static_assert(ITEMS % 4 == 0, "edges are loaded as int4");
   constexpr int TILE = kBlock * ITEMS;
   __shared__ int32_t s_red[kBlock / 32];
@@ -618,27 +679,37 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// Tuning knobs of the sampler chain (environment, read once; defaults are the measured best, profiles/r01d_waves.md):
+// Tuning knobs of the sampler chain (environment, read once; defaults are the measured best, profiles/r01d_sampler_chain.md):
 //   LG_SAMPLE_TILE   frontier entries per CTA of the long hops (32..256)
-//   LG_SAMPLE_MINB   6 = cap the sample kernel at 40 registers so that 6 CTAs fit an SM (one wave for 200 k entries)
-//   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8, 12 or 16)
-//   LG_RANK_MINB     6 = cap the rank kernel at 40 registers
-//   LG_PM_FILL_MB    dense position maps up to this size are released by a streaming fill instead of the O(batch) scatter
-// (A forced shared-memory carve-out on these kernels was measured and rejected: profiles/r01b_overlap.md.)
+//   LG_SAMPLE_MINB   6 (default) = the 256-entry sample kernel of the dense layout is capped at 40 registers so that
+//                    6 CTAs fit an SM: the 782 tiles of a 200 k-entry frontier run as one wave (592 slots otherwise)
+//   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8 or 12; default 12 dense, 8 hashed: one wave)
+//   LG_PM_FILL_MB    dense position maps up to this size (default 16 MB) are released by a streaming fill instead of
+//                    the O(batch) scatter
+//   LG_ROW_PREFETCH  1 (default) = a hop's sample kernel also looks up the rows of the vertices it samples, for the next hop
+// (A forced shared-memory carve-out on these kernels, LG_CARVEOUT, was measured and rejected: profiles/r01b_overlap.md.)
 struct SamplerTune {
-  int sample_tile, sample_minb, rank_items, rank_minb, pm_fill_mb;
+  int sample_tile, sample_minb, rank_items, pm_fill_mb, row_prefetch;
 };
 static const SamplerTune& sampler_tune() {
   static SamplerTune t = [] {
-    SamplerTune x{0, 0, 0, 0, 0};
+    SamplerTune x{0, 6, 0, 16, 1};
     if (const char* e = getenv("LG_SAMPLE_TILE")) x.sample_tile = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_MINB")) x.sample_minb = atoi(e);
     if (const char* e = getenv("LG_RANK_ITEMS")) x.rank_items = atoi(e);
-    if (const char* e = getenv("LG_RANK_MINB")) x.rank_minb = atoi(e);
     if (const char* e = getenv("LG_PM_FILL_MB")) x.pm_fill_mb = atoi(e);
+    if (const char* e = getenv("LG_ROW_PREFETCH")) x.row_prefetch = atoi(e);
     return x;
   }();
   return t;
+}
+
+// PDL on the handle's chain: LG_PDL if set, else on for the dense layout only.  Next to the gather the hashed kernels
+// (multi-wave, L1-hungry) lost 2-7 % with it, the dense ones gained 4-10 % (profiles/r01d_sampler_chain.md).
+static bool pdl_on(const lg_sampler* s, int except_bit = 0) {
+  const int v = lg_pdl();
+  if (v < 0) return !s->hashed;
+  return (v & 1) && !(v & except_bit);
 }
 
 extern "C" int64_t lg_num_ids(int32_t batch_size, const int32_t* fanout, int32_t n_hops) {
@@ -661,11 +732,13 @@ static int pick_tile_f_tuned(int64_t frontier_max) {
   const int t = pick_tile_f(frontier_max), o = sampler_tune().sample_tile;
   return (t == 256 && (o == 32 || o == 64 || o == 128 || o == 256)) ? o : t;
 }
-static int pick_rank_items(int64_t edges_max) {
-  // all tiles of a hop resident at once when possible (6 CTAs x 148 SMs): 8 edges per thread up to ~1.8 M edges
+static int pick_rank_items(int64_t edges_max, bool hashed) {
+  // all tiles of a hop resident at once when possible: 4 edges per thread for short hops; for long ones 12 (dense: 46
+  // registers, 5 CTAs per SM, 652 tiles for 2 M edges) or 8 (hashed: 60 registers; 12 would need 80)
   if (edges_max <= 4ll * kBlock * kSMs * 5) return 4;
   const int o = sampler_tune().rank_items;
-  return (o == 4 || o == 8 || o == 12 || o == 16) ? o : 8;
+  if (o == 4 || o == 8 || o == 12) return o;
+  return hashed ? 8 : 12;
 }
 
 extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
@@ -698,6 +771,13 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
     LG_CUDA(cudaMalloc(&s->gid[b], (size_t)smax * sizeof(int32_t)));
     LG_CUDA(cudaMemset(s->gid[b], 0, (size_t)smax * sizeof(int32_t)));
   }
+  if (n_hops >= 2 && sampler_tune().row_prefetch) {  // frontier row descriptors: as long as the longest consumed frontier
+    const int64_t fmax = s->slots_per_hop[n_hops - 1];
+    for (int b = 0; b < 2; b++) {
+      LG_CUDA(cudaMalloc(&s->row[b], (size_t)fmax * sizeof(u64)));
+      LG_CUDA(cudaMalloc(&s->deg[b], (size_t)fmax * sizeof(int32_t)));
+    }
+  }
   // position map.  DENSE: one word per vertex (the reference's position_map, engine/server.cu:224), 0xFFFFFFFF =
   // absent; HASHED: 2^k >= 1.5 x num_ids packed words.  Dense while the map can stay L2-resident next to the
   // gather's stream (LG_DENSE_MAX_MB, default 48 MB of the 126 MB L2); LG_DEDUP=dense|hash overrides.
@@ -715,8 +795,9 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
     LG_CUDA(cudaMalloc(&s->table, (size_t)slots * sizeof(u64)));
     LG_CUDA(cudaMemset(s->table, 0xFF, (size_t)slots * sizeof(u64)));
   } else {
-    LG_CUDA(cudaMalloc(&s->pm, (size_t)num_nodes * sizeof(uint32_t)));
-    LG_CUDA(cudaMemset(s->pm, 0xFF, (size_t)num_nodes * sizeof(uint32_t)));
+    const size_t pm_words = ((size_t)num_nodes + 3) & ~(size_t)3;  // whole 16-byte words for the streaming fill
+    LG_CUDA(cudaMalloc(&s->pm, pm_words * sizeof(uint32_t)));
+    LG_CUDA(cudaMemset(s->pm, 0xFF, pm_words * sizeof(uint32_t)));
   }
   // small per-batch state
   int64_t bytes = sizeof(HopState) * LG_MAX_HOPS;
@@ -726,17 +807,19 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
     int tf = pick_tile_f_tuned(s->slots_per_hop[h]);
     s->sample_tile_f[h] = tf;
     s->sample_tiles[h] = (int32_t)((s->slots_per_hop[h] + tf - 1) / tf);
-    s->rank_items[h] = pick_rank_items(s->slots_per_hop[h + 1]);
+    s->rank_items[h] = pick_rank_items(s->slots_per_hop[h + 1], s->hashed != 0);
     const int64_t rank_tile = (int64_t)kBlock * s->rank_items[h];
     s->rank_tiles[h] = (int32_t)((s->slots_per_hop[h + 1] + rank_tile - 1) / rank_tile);
     off_state[0][h] = bytes;
     bytes += (int64_t)s->sample_tiles[h] * 8;
+    bytes = (bytes + 127) & ~127ll;
     off_anchor[0][h] = bytes;
-    bytes += (int64_t)(s->sample_tiles[h] / kAnchor + 2) * 8;
+    bytes += (int64_t)(s->sample_tiles[h] / kGroup + 1) * kGroupStride * 8;
     off_state[1][h] = bytes;
     bytes += (int64_t)s->rank_tiles[h] * 8;
+    bytes = (bytes + 127) & ~127ll;
     off_anchor[1][h] = bytes;
-    bytes += (int64_t)(s->rank_tiles[h] / kAnchor + 2) * 8;
+    bytes += (int64_t)(s->rank_tiles[h] / kGroup + 1) * kGroupStride * 8;
   }
   s->small_bytes = bytes;
   LG_CUDA(cudaMalloc(&s->small, (size_t)bytes));
@@ -778,6 +861,10 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaFree(s->gather_ticket);
   cudaFree(s->gid[0]);
   cudaFree(s->gid[1]);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(s->row[b]);
+    cudaFree(s->deg[b]);
+  }
   cudaFree(s->small);
   cudaFree(s->status);
   cudaFreeHost(s->pinned_seeds);
@@ -866,16 +953,17 @@ extern "C" int32_t lg_sampler_dedup_layout(const lg_sampler* s) { return s ? s->
 extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
   if (!s) return 0;
   const int64_t map_bytes = s->hashed ? ((int64_t)s->table_mask + 1) * 8 : s->num_nodes * 4;
-  return map_bytes + 2 * s->slots_per_hop[s->n_hops] * 4 + s->small_bytes + 4;
+  const int64_t row_bytes = s->row[0] ? 2 * s->slots_per_hop[s->n_hops - 1] * 12 : 0;
+  return map_bytes + 2 * s->slots_per_hop[s->n_hops] * 4 + row_bytes + s->small_bytes + 4;
 }
 
 // the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
 static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
   if (!s->hashed) {  // HASHED: the table is re-initialised by the next lg_batch_generate instead
-    if (s->num_nodes * 4 <= (int64_t)sampler_tune().pm_fill_mb * (1ll << 20) && (s->num_nodes & 3) == 0)
-      LG_CUDA(lg_launch_opt(!(lg_pdl() & 2), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->pm, s->num_nodes / 4));
+    if (s->num_nodes * 4 <= (int64_t)sampler_tune().pm_fill_mb * (1ll << 20))
+      LG_CUDA(lg_launch_opt(pdl_on(s, 2), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->pm, (s->num_nodes + 3) / 4));
     else
-      LG_CUDA(lg_launch_opt(!(lg_pdl() & 2), pm_clear_kernel, kSMs * 4, kBlock, 0, st, (const int32_t*)b->ids,
+      LG_CUDA(lg_launch_opt(pdl_on(s, 2), pm_clear_kernel, kSMs * 4, kBlock, 0, st, (const int32_t*)b->ids,
                         (const int32_t*)b->node_counter, s->pm, lg_l2_hints()));
     // the next batch's inserts must not overtake this release when the host enqueues them on another stream
     LG_CUDA(cudaEventRecord(s->ev_clear, st));
@@ -908,7 +996,7 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   }
   if (s->clear_recorded && s->clear_stream != st) LG_CUDA(cudaStreamWaitEvent(st, s->ev_clear, 0));
   if (s->hashed)  // O(batch)-sized table, L2-resident: one streaming fill instead of an O(batch) random clear
-    LG_CUDA(lg_launch_opt(!(lg_pdl() & 4), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->table, ((int64_t)s->table_mask + 1) / 2));
+    LG_CUDA(lg_launch_opt(pdl_on(s, 4), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->table, ((int64_t)s->table_mask + 1) / 2));
   long long done = (long long)batch_size * ((long long)counter + 1);
   int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
   if (size < 0) size = 0;
@@ -918,13 +1006,13 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   const int grid_small = (small_words + kBlock - 1) / kBlock;
   if (grid < grid_small) grid = grid_small < 64 ? grid_small : 64;
   if (s->hashed) {
-    LG_CUDA(lg_launch_opt(!(lg_pdl() & 4), batch_generate_kernel<true>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
+    LG_CUDA(lg_launch_opt(pdl_on(s, 4), batch_generate_kernel<true>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
                       s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
                       small_words, lg_l2_hints()));
-    LG_CUDA(lg_launch(seed_local_kernel, grid, kBlock, 0, st, (const int32_t*)b->ids, (const int32_t*)b->node_counter,
+    LG_CUDA(lg_launch_opt(pdl_on(s), seed_local_kernel, grid, kBlock, 0, st, (const int32_t*)b->ids, (const int32_t*)b->node_counter,
                       s->seed_local, map_of(s), lg_l2_hints()));
   } else {
-    LG_CUDA(lg_launch_opt(!(lg_pdl() & 4), batch_generate_kernel<false>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
+    LG_CUDA(lg_launch_opt(pdl_on(s, 4), batch_generate_kernel<false>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
                       s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
                       small_words, lg_l2_hints()));
   }
@@ -933,33 +1021,29 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   return 0;
 }
 
-template <int RNG, bool HASHED, int MINB>
-static cudaError_t launch_sample_minb(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
+template <int RNG, bool HASHED, bool PRODUCE>
+static cudaError_t launch_sample(bool pdl, int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
   switch (tile_f) {
-    case 256: return lg_launch(sample_hop_kernel<256, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
-    case 128: return lg_launch(sample_hop_kernel<128, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
-    case 64: return lg_launch(sample_hop_kernel<64, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
-    default: return lg_launch(sample_hop_kernel<32, RNG, HASHED, MINB>, grid, kBlock, 0, st, a);
+    case 256:
+      if (!HASHED && !PRODUCE && sampler_tune().sample_minb == 6)
+        return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, false, 6, false>, grid, kBlock, 0, st, a);
+      return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
+    case 128: return lg_launch_opt(pdl, sample_hop_kernel<128, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
+    case 64: return lg_launch_opt(pdl, sample_hop_kernel<64, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
+    default: return lg_launch_opt(pdl, sample_hop_kernel<32, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
   }
 }
 template <int RNG, bool HASHED>
-static cudaError_t launch_sample(int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
-  if (sampler_tune().sample_minb == 6) return launch_sample_minb<RNG, HASHED, 6>(tile_f, grid, st, a);
-  return launch_sample_minb<RNG, HASHED, 0>(tile_f, grid, st, a);
-}
-template <bool HASHED, int MINB>
-static cudaError_t launch_rank_minb(int items, int grid, cudaStream_t st, const RankArgs& r) {
-  switch (items) {
-    case 16: return lg_launch(rank_kernel<16, HASHED, MINB>, grid, kBlock, 0, st, r);
-    case 12: return lg_launch(rank_kernel<12, HASHED, MINB>, grid, kBlock, 0, st, r);
-    case 8: return lg_launch(rank_kernel<8, HASHED, MINB>, grid, kBlock, 0, st, r);
-    default: return lg_launch(rank_kernel<4, HASHED, MINB>, grid, kBlock, 0, st, r);
-  }
+static cudaError_t launch_sample(bool pdl, bool produce, int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
+  return produce ? launch_sample<RNG, HASHED, true>(pdl, tile_f, grid, st, a) : launch_sample<RNG, HASHED, false>(pdl, tile_f, grid, st, a);
 }
 template <bool HASHED>
-static cudaError_t launch_rank(int items, int grid, cudaStream_t st, const RankArgs& r) {
-  if (sampler_tune().rank_minb == 6) return launch_rank_minb<HASHED, 6>(items, grid, st, r);
-  return launch_rank_minb<HASHED, 0>(items, grid, st, r);
+static cudaError_t launch_rank(bool pdl, int items, int grid, cudaStream_t st, const RankArgs& r) {
+  switch (items) {
+    case 12: return lg_launch_opt(pdl, rank_kernel<12, HASHED>, grid, kBlock, 0, st, r);
+    case 8: return lg_launch_opt(pdl, rank_kernel<8, HASHED>, grid, kBlock, 0, st, r);
+    default: return lg_launch_opt(pdl, rank_kernel<4, HASHED>, grid, kBlock, 0, st, r);
+  }
 }
 
 // one hop: sample + rank (+ the hop's own relabel pass unless the caller folds it into the next hop's sample kernel)
@@ -996,12 +1080,25 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   a.k1 = (uint32_t)(rng_seed >> 32);
   a.l2 = lg_l2_hints();
   a.trace = s->trace;
+  // row descriptors: this hop consumes what the previous hop's kernel looked up (same batch, same topology), and
+  // produces them for the next hop
+  const bool consume = hop > 1 && s->row[0] && s->rows_hop == hop - 1 && s->rows_batch == batch_id &&
+                       s->rows_topo[0] == (const void*)topo->indptr[topo->n_parts] && s->rows_topo[1] == (const void*)topo->directory;
+  const bool produce = hop < s->n_hops && s->row[0];
+  a.row_in = consume ? s->row[(h + 1) & 1] : nullptr;
+  a.deg_in = consume ? s->deg[(h + 1) & 1] : nullptr;
+  a.row_out = produce ? s->row[h & 1] : nullptr;
+  a.deg_out = produce ? s->deg[h & 1] : nullptr;
+  s->rows_hop = produce ? hop : 0;
+  s->rows_batch = batch_id;
+  s->rows_topo[0] = (const void*)topo->indptr[topo->n_parts];
+  s->rows_topo[1] = (const void*)topo->directory;
   if (rng_kind == LG_RNG_MINSTD) {
-    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_MINSTD, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
-    else LG_CUDA((launch_sample<LG_RNG_MINSTD, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_MINSTD, true>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_MINSTD, false>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
   } else {
-    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_PHILOX, true>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
-    else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_PHILOX, true>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
   }
   RankArgs r;
   r.gid = s->gid[h & 1];
@@ -1018,15 +1115,15 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   r.l2 = lg_l2_hints();
   r.status = s->status;
   r.trace = s->trace;
-  if (s->hashed) LG_CUDA(launch_rank<true>(s->rank_items[h], s->rank_tiles[h], st, r));
-  else LG_CUDA(launch_rank<false>(s->rank_items[h], s->rank_tiles[h], st, r));
+  if (s->hashed) LG_CUDA(launch_rank<true>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r));
+  else LG_CUDA(launch_rank<false>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r));
   if (relabel_own) {
     const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
     if (s->hashed)
-      LG_CUDA(lg_launch(relabel_kernel<true>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
+      LG_CUDA(lg_launch_opt(pdl_on(s), relabel_kernel<true>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
                         (const int32_t*)b->edge_counter, map_of(s), lg_l2_hints()));
     else
-      LG_CUDA(lg_launch(relabel_kernel<false>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
+      LG_CUDA(lg_launch_opt(pdl_on(s), relabel_kernel<false>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
                         (const int32_t*)b->edge_counter, map_of(s), lg_l2_hints()));
   }
   return 0;
@@ -1054,7 +1151,7 @@ extern "C" int lg_io_complete(lg_sampler* s, lg_stream_t stream_, int32_t mode, 
   LG_REQUIRE(s && b, "lg_io_complete: null argument");
   cudaStream_t st = (cudaStream_t)stream_;
   if (mode == LG_TRAINMODE && node_hotness) {  // :558
-    LG_CUDA(lg_launch(hotness_measure_kernel, kSMs * 2, kBlock, 0, st, (const int32_t*)b->ids,
+    LG_CUDA(lg_launch_opt(pdl_on(s), hotness_measure_kernel, kSMs * 2, kBlock, 0, st, (const int32_t*)b->ids,
                       (const int32_t*)b->node_counter, (u64*)node_hotness, max_ids));
   }
   // ClearPosMap: the reference clears in train mode only (its bitmap makes stale entries harmless in the
