@@ -251,11 +251,7 @@ struct SampleArgs {
   lg_topology topo;
   const int32_t* frontier_prev;  // hop > 1: global ids of the previous hop's sampled sources
   const int32_t* seed_local;     // HASHED: batch-local ids of the seeds (seed_local_kernel)
-  const u64* row_in;             // hop > 1: row descriptors of the frontier written by the previous hop (or null)
-  const int32_t* deg_in;
   int32_t* gid_out;              // this hop's sampled sources (global ids), hop-relative positions
-  u64* row_out;                  // PRODUCE: row descriptor (part << 56 | first edge) and degree of every sampled
-  int32_t* deg_out;              //          source = the next hop's frontier, so that hop starts without a lookup
   int32_t* ids;
   int32_t* agg_src;
   int32_t* agg_dst;
@@ -270,12 +266,11 @@ struct SampleArgs {
   int32_t fanout;
   uint32_t fanout_magic;  // ceil(2^32 / fanout): slot / fanout as one multiply-high (slot < 2^16)
   int32_t relabel_prev;   // also write the previous hop's agg_src (its construct_graph) from the position map
+  int32_t precheck;       // DENSE: L1-cached look at the map word before the RED.MIN (LG_RED_PRECHECK)
   uint32_t batch_id, stream_id, k0, k1;
   int32_t l2;  // lg_l2_hints()
   u64* trace;
 };
-
-constexpr u64 kRowMask = (1ull << 56) - 1;
 
 // Row of vertex v: (part, first edge, degree) through the topology directory (FindTopo, cache/cache.cu:217-225)
 __device__ __forceinline__ void row_locate(const lg_topology& t, int32_t v, int32_t loc, int* part, long long* row) {
@@ -287,7 +282,7 @@ __device__ __forceinline__ void row_locate(const lg_topology& t, int32_t v, int3
   }
 }
 
-template <int TILE_F, int RNG, bool HASHED, int MINB, bool PRODUCE>
+template <int TILE_F, int RNG, bool HASHED, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleArgs a) {
   static_assert(TILE_F <= kBlock, "one thread per frontier entry of the tile");
   __shared__ long long s_start[TILE_F];
@@ -320,9 +315,7 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
   const int32_t c = a.fanout;
   const int32_t i0 = tile * TILE_F;
 
-  // 1. rows of the tile's frontier entries.  For hop > 1 the previous hop's sample kernel already looked them up
-  //    (row_in/deg_in, written next to gid_out): this phase is then two coalesced loads, and the chained prefix below —
-  //    which every later tile waits for — no longer sits behind a tail of dependent random reads.
+  // 1. row lookup for the tile's frontier entries
   int32_t cnt = 0, fl = 0;
   bool live = false;
   if (tid < TILE_F) {
@@ -341,18 +334,11 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
         else
           fl = (int32_t)map_lookup<false>(a.map, (uint32_t)v, keep);
         int part;
-        if (a.row_in) {
-          const u64 r = a.row_in[i];
-          part = (int)(r >> 56);
-          start = (long long)(r & kRowMask);
-          deg = a.deg_in[i];
-        } else {
-          long long row;
-          row_locate(a.topo, v, a.topo.directory ? ld_nc_s32_hint(a.topo.directory + v, keep) : -1, &part, &row);
-          const int64_t* ip = a.topo.indptr[part];
-          start = ld_nc_s64_hint(ip + row, keep);
-          deg = (int32_t)(ld_nc_s64_hint(ip + row + 1, keep) - start);  // :226 (int32 col_size)
-        }
+        long long row;
+        row_locate(a.topo, v, a.topo.directory ? ld_nc_s32_hint(a.topo.directory + v, keep) : -1, &part, &row);
+        const int64_t* ip = a.topo.indptr[part];
+        start = ld_nc_s64_hint(ip + row, keep);
+        deg = (int32_t)(ld_nc_s64_hint(ip + row + 1, keep) - start);  // :226 (int32 col_size)
         ind = a.topo.indices[part];
         cnt = deg < c ? deg : c;
         if (cnt < 0) cnt = 0;
@@ -453,6 +439,22 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
           }
         }
       }
+    } else if (a.precheck) {
+      // a word that already holds an earlier position (or a final id) needs no RED: hub vertices are sampled thousands
+      // of times per hop, and their REDs serialise on one L2 slice.  A stale L1 line only holds a LARGER value than
+      // the word has now (values only decrease while a hop is open), so skipping on `cur <= val` is always right.
+      uint32_t cur[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) cur[u] = (p[u] >= 0) ? ld_ca_u32_hint(a.map.pm + w[u], keep) : 0u;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (p[u] >= 0) {
+          a.gid_out[p[u]] = w[u];
+          a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
+          const uint32_t val = kNewBit | (uint32_t)p[u];
+          if (cur[u] > val) red_min_u32_hint(a.map.pm + w[u], val, keep);
+        }
+      }
     } else {
 #pragma unroll
       for (int u = 0; u < U; u++) {
@@ -460,31 +462,6 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
           a.gid_out[p[u]] = w[u];
           a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
           red_min_u32_hint(a.map.pm + w[u], kNewBit | (uint32_t)p[u], keep);
-        }
-      }
-    }
-    if (PRODUCE) {  // the sampled sources are the next hop's frontier: look their rows up now, U at a time
-      int32_t loc[U];
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        loc[u] = (p[u] >= 0 && a.topo.directory) ? ld_nc_s32_hint(a.topo.directory + w[u], keep) : -1;
-      long long e0[U], e1[U];
-      int part[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (p[u] >= 0) {
-          long long row;
-          row_locate(a.topo, w[u], loc[u], &part[u], &row);
-          const int64_t* ip = a.topo.indptr[part[u]];
-          e0[u] = ld_nc_s64_hint(ip + row, keep);
-          e1[u] = ld_nc_s64_hint(ip + row + 1, keep);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (p[u] >= 0) {
-          a.row_out[p[u]] = ((u64)part[u] << 56) | (u64)e0[u];
-          a.deg_out[p[u]] = (int32_t)(e1[u] - e0[u]);
         }
       }
     }
@@ -508,15 +485,21 @@ struct RankArgs {
   u64* tile_state;
   u64* anchors;
   HopState* hs;
+  int32_t* agg_src;  // non-null: also write this hop's agg_src (construct_graph) as far as this pass knows it
   int32_t hop;
-  int32_t publish;  // write the final local ids back into the map (needed by the next hop / the relabel pass)
   int32_t ids_cap;
   int32_t l2;
   int32_t* status;
   u64* trace;
 };
 
-template <int ITEMS, bool HASHED>
+// PUBLISH: write the final local ids back into the map — needed while a later hop will insert into it (its RED.MIN
+// must lose against a final id) or look frontier vertices up; not after the last hop.
+// agg_src (construct_graph, :283-296) is resolved here for two of three kinds of edges: the source was already in the
+// batch before this hop (the map word IS its local id), or this edge is the source's first occurrence (it gets the id
+// assigned below).  A later occurrence of a vertex that is new in this hop only knows the position p_first of the first
+// one: it stores ~p_first, and relabel_kernel replaces it by agg_src[p_first] once every tile is done.
+template <int ITEMS, bool HASHED, bool PUBLISH>
 __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
   static_assert(ITEMS % 4 == 0, "edges are loaded as int4");
   constexpr int TILE = kBlock * ITEMS;
@@ -528,6 +511,7 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
   if (tid == 0) s_tile = atomicAdd(&a.hs->rank_ticket, 1);
   const int32_t E = a.ec[2];
   const int32_t node_base = a.nc[0] + a.nc[1];  // :268
+  const int32_t edge_base = a.ec[0] + a.ec[1];  // :275 (the counters move on when the last CTA is done)
   __syncthreads();
   const int tile = s_tile;
   const int tslot = (a.hop - 1) * 2 + 1;
@@ -545,17 +529,21 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
     }
     // L1-cached: a line fetched before the owner publishes holds kNewBit|p_first, one fetched after holds the
     // final id — neither can equal kNewBit|p for a non-owner, and an owner's word is only rewritten by itself
-    uint32_t sl[HASHED ? ITEMS : 1];
+    uint32_t sl[(HASHED && PUBLISH) ? ITEMS : 1];
     if (HASHED) {
       u64 cur[ITEMS];
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) {  // first probes in flight together
-        sl[k] = map_home(a.map, (uint32_t)w[k]);
-        cur[k] = (p0 + k < E) ? ld_ca_u64_hint(a.map.table + sl[k], keep) : 0ull;
+        const uint32_t home = map_home(a.map, (uint32_t)w[k]);
+        if (PUBLISH) sl[k] = home;
+        cur[k] = (p0 + k < E) ? ld_ca_u64_hint(a.map.table + home, keep) : 0ull;
       }
 #pragma unroll
-      for (int k = 0; k < ITEMS; k++)
-        q[k] = (p0 + k < E) ? table_find_finish(a.map, (uint32_t)w[k], &sl[k], cur[k], keep) : 0u;
+      for (int k = 0; k < ITEMS; k++) {
+        uint32_t slot = PUBLISH ? sl[k] : map_home(a.map, (uint32_t)w[k]);
+        q[k] = (p0 + k < E) ? table_find_finish(a.map, (uint32_t)w[k], &slot, cur[k], keep) : 0u;
+        if (PUBLISH) sl[k] = slot;
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) q[k] = (p0 + k < E) ? ld_ca_u32_hint(a.map.pm + w[k], keep) : 0u;
@@ -564,6 +552,12 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
 #pragma unroll
     for (int k = 0; k < ITEMS; k++)
       if (p0 + k < E && q[k] == (kNewBit | (uint32_t)(p0 + k))) mask |= 1u << k;
+    if (a.agg_src) {  // everything but the first occurrences is known now: q is dead before the scan (registers)
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++)
+        if (p0 + k < E && !(mask & (1u << k)))
+          a.agg_src[edge_base + p0 + k] = (q[k] < kNewBit) ? (int32_t)q[k] : ~(int32_t)(q[k] & ~kNewBit);  // known id, or ~p_first
+    }
     if (tid == 0) trace_mark(a.trace, tslot, tile, 1);
     int32_t total;
     const int32_t mine = block_exclusive_scan(__popc(mask), s_red, &total);
@@ -577,10 +571,11 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
       if (mask & (1u << k)) {
         if (local < a.ids_cap) a.ids[local] = w[k];  // :270
         else *a.status = 1;
-        if (a.publish) {  // position_map :271
+        if (PUBLISH) {  // position_map :271
           if (HASHED) st_u64_hint(a.map.table + sl[k], map_pack((uint32_t)w[k], (uint32_t)local), keep);
           else st_u32_hint(a.map.pm + w[k], (uint32_t)local, keep);
         }
+        if (a.agg_src) a.agg_src[edge_base + p0 + k] = local;
         local++;
       }
     }
@@ -615,25 +610,24 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
   }
 }
 
-// construct_graph for the sources of the hop just ranked (:283-296): agg_src[e] = position_map[src].  Runs after the
-// rank kernel's counter_update: (ec[0], ec[1]) = (offset, count) of the hop's edges.  For every hop but the last
-// lg_run_batch folds this pass into the next hop's sample kernel (which reads the same words anyway).
-template <bool HASHED>
-__global__ void __launch_bounds__(kBlock) relabel_kernel(const int32_t* __restrict__ gid, int32_t* __restrict__ agg_src,
-                                                         const int32_t* __restrict__ ec, const DedupMap map, int32_t l2) {
+// construct_graph for the sources of the hop just ranked (:283-296), second half: the rank kernel left ~p_first in the
+// agg_src entries of later occurrences of vertices that are new in this hop; the first occurrence's entry holds the id.
+// Runs after the rank kernel's counter_update: (ec[0], ec[1]) = (offset, count) of the hop's edges.  Entries that are
+// read (first occurrences, >= 0) are never written here.  For every hop but the last, lg_run_batch (dense layout) folds
+// construct_graph into the next hop's sample kernel instead (which looks the same vertices up anyway).
+__global__ void __launch_bounds__(kBlock) relabel_kernel(int32_t* __restrict__ agg_src, const int32_t* __restrict__ ec) {
   pdl_prologue();
-  const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   const int32_t off = ec[0], E = ec[1];
   const int32_t p0 = (blockIdx.x * kBlock + threadIdx.x) * 4;
   if (p0 >= E) return;
-  const int4 v = *reinterpret_cast<const int4*>(gid + p0);
-  const int32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t q[4];
+  int32_t x[4], y[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) q[k] = (p0 + k < E) ? map_lookup<HASHED>(map, (uint32_t)w[k], keep) : 0u;
+  for (int k = 0; k < 4; k++) x[k] = (p0 + k < E) ? agg_src[off + p0 + k] : 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) y[k] = (x[k] < 0) ? __ldcg(agg_src + off + ~x[k]) : x[k];
 #pragma unroll
   for (int k = 0; k < 4; k++)
-    if (p0 + k < E) agg_src[off + p0 + k] = (int32_t)q[k];
+    if (x[k] < 0) agg_src[off + p0 + k] = y[k];
 }
 
 // ClearPosMap (:542-548): the position-map words of this batch's vertices go back to "not in the batch".
@@ -686,10 +680,13 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8 or 12; default 12 dense, 8 hashed: one wave)
 //   LG_PM_FILL_MB    dense position maps up to this size (default 16 MB) are released by a streaming fill instead of
 //                    the O(batch) scatter
-//   LG_ROW_PREFETCH  1 (default) = a hop's sample kernel also looks up the rows of the vertices it samples, for the next hop
+//   LG_RED_PRECHECK  1 (default) = dense layout: L1-cached look at the map word before the RED.MIN; skips the RED when the
+//                    word already holds an earlier position (hub vertices: sample hop 2 0.0915 -> 0.0827 ms)
+//   (having a hop's sample kernel also look up the rows of the vertices it samples, so that the next hop starts from two
+//   coalesced arrays, was measured and rejected: hop 1 +5 us, hop 2 -2 us)
 // (A forced shared-memory carve-out on these kernels, LG_CARVEOUT, was measured and rejected: profiles/r01b_overlap.md.)
 struct SamplerTune {
-  int sample_tile, sample_minb, rank_items, pm_fill_mb, row_prefetch;
+  int sample_tile, sample_minb, rank_items, pm_fill_mb, red_precheck;
 };
 static const SamplerTune& sampler_tune() {
   static SamplerTune t = [] {
@@ -698,7 +695,7 @@ static const SamplerTune& sampler_tune() {
     if (const char* e = getenv("LG_SAMPLE_MINB")) x.sample_minb = atoi(e);
     if (const char* e = getenv("LG_RANK_ITEMS")) x.rank_items = atoi(e);
     if (const char* e = getenv("LG_PM_FILL_MB")) x.pm_fill_mb = atoi(e);
-    if (const char* e = getenv("LG_ROW_PREFETCH")) x.row_prefetch = atoi(e);
+    if (const char* e = getenv("LG_RED_PRECHECK")) x.red_precheck = atoi(e);
     return x;
   }();
   return t;
@@ -770,13 +767,6 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   for (int b = 0; b < 2; b++) {
     LG_CUDA(cudaMalloc(&s->gid[b], (size_t)smax * sizeof(int32_t)));
     LG_CUDA(cudaMemset(s->gid[b], 0, (size_t)smax * sizeof(int32_t)));
-  }
-  if (n_hops >= 2 && sampler_tune().row_prefetch) {  // frontier row descriptors: as long as the longest consumed frontier
-    const int64_t fmax = s->slots_per_hop[n_hops - 1];
-    for (int b = 0; b < 2; b++) {
-      LG_CUDA(cudaMalloc(&s->row[b], (size_t)fmax * sizeof(u64)));
-      LG_CUDA(cudaMalloc(&s->deg[b], (size_t)fmax * sizeof(int32_t)));
-    }
   }
   // position map.  DENSE: one word per vertex (the reference's position_map, engine/server.cu:224), 0xFFFFFFFF =
   // absent; HASHED: 2^k >= 1.5 x num_ids packed words.  Dense while the map can stay L2-resident next to the
@@ -861,10 +851,6 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaFree(s->gather_ticket);
   cudaFree(s->gid[0]);
   cudaFree(s->gid[1]);
-  for (int b = 0; b < 2; b++) {
-    cudaFree(s->row[b]);
-    cudaFree(s->deg[b]);
-  }
   cudaFree(s->small);
   cudaFree(s->status);
   cudaFreeHost(s->pinned_seeds);
@@ -953,8 +939,7 @@ extern "C" int32_t lg_sampler_dedup_layout(const lg_sampler* s) { return s ? s->
 extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
   if (!s) return 0;
   const int64_t map_bytes = s->hashed ? ((int64_t)s->table_mask + 1) * 8 : s->num_nodes * 4;
-  const int64_t row_bytes = s->row[0] ? 2 * s->slots_per_hop[s->n_hops - 1] * 12 : 0;
-  return map_bytes + 2 * s->slots_per_hop[s->n_hops] * 4 + row_bytes + s->small_bytes + 4;
+  return map_bytes + 2 * s->slots_per_hop[s->n_hops] * 4 + s->small_bytes + 4;
 }
 
 // the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
@@ -1021,28 +1006,24 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   return 0;
 }
 
-template <int RNG, bool HASHED, bool PRODUCE>
+template <int RNG, bool HASHED>
 static cudaError_t launch_sample(bool pdl, int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
   switch (tile_f) {
     case 256:
-      if (!HASHED && !PRODUCE && sampler_tune().sample_minb == 6)
-        return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, false, 6, false>, grid, kBlock, 0, st, a);
-      return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
-    case 128: return lg_launch_opt(pdl, sample_hop_kernel<128, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
-    case 64: return lg_launch_opt(pdl, sample_hop_kernel<64, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
-    default: return lg_launch_opt(pdl, sample_hop_kernel<32, RNG, HASHED, 0, PRODUCE>, grid, kBlock, 0, st, a);
+      if (!HASHED && sampler_tune().sample_minb == 6)
+        return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, false, 6>, grid, kBlock, 0, st, a);
+      return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, HASHED, 0>, grid, kBlock, 0, st, a);
+    case 128: return lg_launch_opt(pdl, sample_hop_kernel<128, RNG, HASHED, 0>, grid, kBlock, 0, st, a);
+    case 64: return lg_launch_opt(pdl, sample_hop_kernel<64, RNG, HASHED, 0>, grid, kBlock, 0, st, a);
+    default: return lg_launch_opt(pdl, sample_hop_kernel<32, RNG, HASHED, 0>, grid, kBlock, 0, st, a);
   }
 }
-template <int RNG, bool HASHED>
-static cudaError_t launch_sample(bool pdl, bool produce, int tile_f, int grid, cudaStream_t st, const SampleArgs& a) {
-  return produce ? launch_sample<RNG, HASHED, true>(pdl, tile_f, grid, st, a) : launch_sample<RNG, HASHED, false>(pdl, tile_f, grid, st, a);
-}
-template <bool HASHED>
+template <bool HASHED, bool PUBLISH>
 static cudaError_t launch_rank(bool pdl, int items, int grid, cudaStream_t st, const RankArgs& r) {
   switch (items) {
-    case 12: return lg_launch_opt(pdl, rank_kernel<12, HASHED>, grid, kBlock, 0, st, r);
-    case 8: return lg_launch_opt(pdl, rank_kernel<8, HASHED>, grid, kBlock, 0, st, r);
-    default: return lg_launch_opt(pdl, rank_kernel<4, HASHED>, grid, kBlock, 0, st, r);
+    case 12: return lg_launch_opt(pdl, rank_kernel<12, HASHED, PUBLISH>, grid, kBlock, 0, st, r);
+    case 8: return lg_launch_opt(pdl, rank_kernel<8, HASHED, PUBLISH>, grid, kBlock, 0, st, r);
+    default: return lg_launch_opt(pdl, rank_kernel<4, HASHED, PUBLISH>, grid, kBlock, 0, st, r);
   }
 }
 
@@ -1074,31 +1055,19 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   a.fanout = s->fanout[h];
   a.fanout_magic = (uint32_t)(((1ull << 32) + (uint64_t)s->fanout[h] - 1) / (uint64_t)s->fanout[h]);
   a.relabel_prev = relabel_prev ? 1 : 0;
+  a.precheck = sampler_tune().red_precheck;
   a.batch_id = batch_id;
   a.stream_id = stream_id;
   a.k0 = (uint32_t)rng_seed;
   a.k1 = (uint32_t)(rng_seed >> 32);
   a.l2 = lg_l2_hints();
   a.trace = s->trace;
-  // row descriptors: this hop consumes what the previous hop's kernel looked up (same batch, same topology), and
-  // produces them for the next hop
-  const bool consume = hop > 1 && s->row[0] && s->rows_hop == hop - 1 && s->rows_batch == batch_id &&
-                       s->rows_topo[0] == (const void*)topo->indptr[topo->n_parts] && s->rows_topo[1] == (const void*)topo->directory;
-  const bool produce = hop < s->n_hops && s->row[0];
-  a.row_in = consume ? s->row[(h + 1) & 1] : nullptr;
-  a.deg_in = consume ? s->deg[(h + 1) & 1] : nullptr;
-  a.row_out = produce ? s->row[h & 1] : nullptr;
-  a.deg_out = produce ? s->deg[h & 1] : nullptr;
-  s->rows_hop = produce ? hop : 0;
-  s->rows_batch = batch_id;
-  s->rows_topo[0] = (const void*)topo->indptr[topo->n_parts];
-  s->rows_topo[1] = (const void*)topo->directory;
   if (rng_kind == LG_RNG_MINSTD) {
-    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_MINSTD, true>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
-    else LG_CUDA((launch_sample<LG_RNG_MINSTD, false>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_MINSTD, true>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_MINSTD, false>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
   } else {
-    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_PHILOX, true>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
-    else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(pdl_on(s), produce, s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_PHILOX, true>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
   }
   RankArgs r;
   r.gid = s->gid[h & 1];
@@ -1106,7 +1075,7 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   r.nc = b->node_counter;
   r.ec = b->edge_counter;
   r.map = map_of(s);
-  r.publish = 1;
+  r.agg_src = relabel_own ? b->agg_src : nullptr;
   r.tile_state = s->rank_state[h];
   r.anchors = s->rank_anchor[h];
   r.hs = s->hs + h;
@@ -1115,16 +1084,17 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   r.l2 = lg_l2_hints();
   r.status = s->status;
   r.trace = s->trace;
-  if (s->hashed) LG_CUDA(launch_rank<true>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r));
-  else LG_CUDA(launch_rank<false>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r));
+  const bool publish = hop < s->n_hops;  // a later hop inserts into / reads the map
+  if (s->hashed) {
+    if (publish) LG_CUDA((launch_rank<true, true>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
+    else LG_CUDA((launch_rank<true, false>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
+  } else {
+    if (publish) LG_CUDA((launch_rank<false, true>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
+    else LG_CUDA((launch_rank<false, false>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
+  }
   if (relabel_own) {
     const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
-    if (s->hashed)
-      LG_CUDA(lg_launch_opt(pdl_on(s), relabel_kernel<true>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
-                        (const int32_t*)b->edge_counter, map_of(s), lg_l2_hints()));
-    else
-      LG_CUDA(lg_launch_opt(pdl_on(s), relabel_kernel<false>, (int)grid, kBlock, 0, st, (const int32_t*)s->gid[h & 1], b->agg_src,
-                        (const int32_t*)b->edge_counter, map_of(s), lg_l2_hints()));
+    LG_CUDA(lg_launch_opt(pdl_on(s), relabel_kernel, (int)grid, kBlock, 0, st, b->agg_src, (const int32_t*)b->edge_counter));
   }
   return 0;
 }

@@ -30,11 +30,6 @@ struct lg_sampler {
   cudaStream_t clear_stream;   // another stream than the next lg_batch_generate: engine/server.cu puts it on stream 2)
   int32_t clear_recorded;
   int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)
-  u64* row[2];           // row descriptors (part << 56 | first edge) of the same frontier entries, written by the hop
-  int32_t* deg[2];       // that sampled them (and their degrees) so the next hop starts without a row lookup
-  int32_t rows_hop;      // hop whose sample kernel filled row[]/deg[] last (0 = none), and the topology it read
-  const void* rows_topo[2];
-  uint32_t rows_batch;
   uint8_t* small;        // memset-per-batch region: HopState[hops] + chained-scan tile states
   int64_t small_bytes;
   HopState* hs;
