@@ -2,18 +2,22 @@
 //
 // Replaces, per hop, the reference's chain  FindTopo (2 bcht probes) -> random_sample ->
 // construct_graph -> counter_update (+ 2 blocking D2H copies)   [engine/operator_impl.cu:175-296,
-// 400-499; cache/cache.cu:217-225]  with TWO launches and no host synchronisation:
+// 400-499; cache/cache.cu:217-225]  with two or three launches and no host synchronisation:
 //
 //   sample_hop_kernel   tile of frontier entries -> row lookup (directory -> HBM shard / peer
-//                       shard / host UVA), per-entry edge count min(deg, fanout), chained scan
-//                       (decoupled look-back) for the canonical edge offsets, with-replacement
+//                       shard / host UVA), per-entry edge count min(deg, fanout), block scan + two-level
+//                       prefix over the earlier tiles for the canonical edge offsets, with-replacement
 //                       pick (Philox4x32-10 or the reference's minstd stream), edge emission in
 //                       ascending slot order, RED.MIN of (kNewBit | first edge position) into the
 //                       position map word of the sampled vertex.  For hop > 1 it also writes the
 //                       previous hop's agg_src (construct_graph) — it reads those words anyway.
 //   rank_kernel         first-occurrence flags -> scan -> batch-local ids in first-seen order, `ids`
-//                       append, position-map publish, the op's counter_update by the last CTA.
-//   relabel_kernel      last hop only: agg_src[e] = position_map[src] (construct_graph).
+//                       append, position-map publish (not after the last hop), the op's counter_update by
+//                       the last CTA; optionally agg_src of the hop: the local id where this pass knows it,
+//                       ~p_first for later occurrences of vertices that are new in the hop.
+//   relabel_kernel      where rank wrote agg_src: agg_src[e] = agg_src[p_first] for the ~p_first entries.
+//
+// The kernels of a batch are chained with programmatic dependent launch (pdl_prologue, common.cuh).
 //
 // Dedup state ("position map": vertex -> kNewBit | first edge position while a hop is open, batch-local id
 // afterwards), two layouts chosen per handle by the size of the graph (lg_sampler_create):
@@ -520,43 +524,47 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
 
   if (tile < n_tiles) {
     const int32_t p0 = tile * TILE + tid * ITEMS;  // ITEMS consecutive edges per thread
-    int32_t w[ITEMS];
-    uint32_t q[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; k += 4) {  // the buffer is padded to a multiple of TILE, reads past E are discarded
-      const int4 v = *reinterpret_cast<const int4*>(a.gid + p0 + k);
-      w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
-    }
-    // L1-cached: a line fetched before the owner publishes holds kNewBit|p_first, one fetched after holds the
-    // final id — neither can equal kNewBit|p for a non-owner, and an owner's word is only rewritten by itself
-    uint32_t sl[(HASHED && PUBLISH) ? ITEMS : 1];
-    if (HASHED) {
-      u64 cur[ITEMS];
-#pragma unroll
-      for (int k = 0; k < ITEMS; k++) {  // first probes in flight together
-        const uint32_t home = map_home(a.map, (uint32_t)w[k]);
-        if (PUBLISH) sl[k] = home;
-        cur[k] = (p0 + k < E) ? ld_ca_u64_hint(a.map.table + home, keep) : 0ull;
-      }
-#pragma unroll
-      for (int k = 0; k < ITEMS; k++) {
-        uint32_t slot = PUBLISH ? sl[k] : map_home(a.map, (uint32_t)w[k]);
-        q[k] = (p0 + k < E) ? table_find_finish(a.map, (uint32_t)w[k], &slot, cur[k], keep) : 0u;
-        if (PUBLISH) sl[k] = slot;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < ITEMS; k++) q[k] = (p0 + k < E) ? ld_ca_u32_hint(a.map.pm + w[k], keep) : 0u;
-    }
+    // The edges are looked up in chunks of CH (all probes of a chunk in flight together) and only a bit per edge
+    // survives the chunk.  HASHED: chunks of 8 — with the vertices, 64-bit table words and slots of all ITEMS edges
+    // live at once the kernel needed 60-120 registers and its tiles ran in 1.65 waves.  DENSE: one chunk (every lookup
+    // of the thread in flight together; chunks of 4 were measured 10 % slower per launch).
+    constexpr int CH = HASHED ? ((ITEMS % 8 == 0) ? 8 : 4) : ITEMS;
     uint32_t mask = 0;
+#pragma unroll 1
+    for (int c = 0; c < ITEMS; c += CH) {
+      int32_t w[CH];
+      uint32_t q[CH];
 #pragma unroll
-    for (int k = 0; k < ITEMS; k++)
-      if (p0 + k < E && q[k] == (kNewBit | (uint32_t)(p0 + k))) mask |= 1u << k;
-    if (a.agg_src) {  // everything but the first occurrences is known now: q is dead before the scan (registers)
+      for (int k = 0; k < CH; k += 4) {  // the buffer is padded to a multiple of TILE, reads past E are discarded
+        const int4 v = *reinterpret_cast<const int4*>(a.gid + p0 + c + k);
+        w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
+      }
+      // L1-cached: a line fetched before the owner publishes holds kNewBit|p_first, one fetched after holds the
+      // final id — neither can equal kNewBit|p for a non-owner, and an owner's word is only rewritten by itself
+      if (HASHED) {
+        u64 cur[CH];
+        uint32_t sl[CH];
 #pragma unroll
-      for (int k = 0; k < ITEMS; k++)
-        if (p0 + k < E && !(mask & (1u << k)))
-          a.agg_src[edge_base + p0 + k] = (q[k] < kNewBit) ? (int32_t)q[k] : ~(int32_t)(q[k] & ~kNewBit);  // known id, or ~p_first
+        for (int k = 0; k < CH; k++) {  // first probes in flight together
+          sl[k] = map_home(a.map, (uint32_t)w[k]);
+          cur[k] = (p0 + c + k < E) ? ld_ca_u64_hint(a.map.table + sl[k], keep) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k++)
+          q[k] = (p0 + c + k < E) ? table_find_finish(a.map, (uint32_t)w[k], &sl[k], cur[k], keep) : 0u;
+      } else {
+#pragma unroll
+        for (int k = 0; k < CH; k++) q[k] = (p0 + c + k < E) ? ld_ca_u32_hint(a.map.pm + w[k], keep) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        const int32_t p = p0 + c + k;
+        if (p < E) {
+          if (q[k] == (kNewBit | (uint32_t)p)) mask |= 1u << (c + k);
+          else if (a.agg_src)  // everything but the first occurrences is known now: the local id, or ~p_first
+            a.agg_src[edge_base + p] = (q[k] < kNewBit) ? (int32_t)q[k] : ~(int32_t)(q[k] & ~kNewBit);
+        }
+      }
     }
     if (tid == 0) trace_mark(a.trace, tslot, tile, 1);
     int32_t total;
@@ -566,18 +574,23 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
     if (tid == 0 && tile == n_tiles - 1) a.hs->new_nodes = excl + total;  // C_h (:263)
     if (tid == 0) trace_mark(a.trace, tslot, tile, 3);
     int32_t local = node_base + excl + mine;
-#pragma unroll
-    for (int k = 0; k < ITEMS; k++) {
-      if (mask & (1u << k)) {
-        if (local < a.ids_cap) a.ids[local] = w[k];  // :270
-        else *a.status = 1;
-        if (PUBLISH) {  // position_map :271
-          if (HASHED) st_u64_hint(a.map.table + sl[k], map_pack((uint32_t)w[k], (uint32_t)local), keep);
-          else st_u32_hint(a.map.pm + w[k], (uint32_t)local, keep);
+    while (mask) {  // first occurrences, in edge order; the vertex is re-read (coalesced, cached) rather than kept
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int32_t w = a.gid[p0 + k];
+      if (local < a.ids_cap) a.ids[local] = w;  // :270
+      else *a.status = 1;
+      if (PUBLISH) {  // position_map :271
+        if (HASHED) {
+          uint32_t slot = map_home(a.map, (uint32_t)w);
+          table_find_finish(a.map, (uint32_t)w, &slot, ld_ca_u64_hint(a.map.table + slot, keep), keep);
+          st_u64_hint(a.map.table + slot, map_pack((uint32_t)w, (uint32_t)local), keep);
+        } else {
+          st_u32_hint(a.map.pm + w, (uint32_t)local, keep);
         }
-        if (a.agg_src) a.agg_src[edge_base + p0 + k] = local;
-        local++;
       }
+      if (a.agg_src) a.agg_src[edge_base + p0 + k] = local;
+      local++;
     }
     if (tid == 0) trace_mark(a.trace, tslot, tile, 4);
   }
@@ -610,13 +623,44 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
   }
 }
 
+// Release of the batch's position-map words (ClearPosMap, :542-548), as a device-side step that the last kernel of a
+// batch can run itself (lg_run_batch): one kernel launch less per batch — every launch on the GPU stalls the gather
+// streaming on the other stream for ~4 us, whatever its size (profiles/r01d_overlap.md).
+struct ReleaseArgs {
+  uint4* fill;  // non-null: streaming fill of n16 16-byte words with all ones (small dense maps, the hashed table)
+  int64_t n16;
+  uint32_t* pm;  // else non-null: O(batch) scatter over the batch's vertices
+  const int32_t* ids;
+  const int32_t* nc;
+  int32_t l2;
+};
+__device__ __forceinline__ void release_map(const ReleaseArgs& r) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  if (r.fill) {
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    for (int64_t i = t; i < r.n16; i += nt) r.fill[i] = ones;
+  } else if (r.pm) {
+    const u64 keep = l2_policy((r.l2 & 4) ? 1 : 0);
+    int32_t n = r.nc[LG_INTRABATCH_CON * 2 + 1];
+    const int32_t seeds = r.nc[LG_INTRABATCH_CON * 3];
+    if (seeds > n) n = seeds;  // before the first hop nc[7] is still 0
+    for (int64_t i = t; i < n; i += nt) {
+      const int32_t v = r.ids[i];
+      if (v >= 0) st_u32_hint(r.pm + v, kPmEmpty, keep);
+    }
+  }
+}
+
 // construct_graph for the sources of the hop just ranked (:283-296), second half: the rank kernel left ~p_first in the
 // agg_src entries of later occurrences of vertices that are new in this hop; the first occurrence's entry holds the id.
 // Runs after the rank kernel's counter_update: (ec[0], ec[1]) = (offset, count) of the hop's edges.  Entries that are
 // read (first occurrences, >= 0) are never written here.  For every hop but the last, lg_run_batch (dense layout) folds
 // construct_graph into the next hop's sample kernel instead (which looks the same vertices up anyway).
-__global__ void __launch_bounds__(kBlock) relabel_kernel(int32_t* __restrict__ agg_src, const int32_t* __restrict__ ec) {
+// After the last hop nobody reads the position map again: lg_run_batch lets this kernel release it (`rel`).
+__global__ void __launch_bounds__(kBlock) relabel_kernel(int32_t* __restrict__ agg_src, const int32_t* __restrict__ ec,
+                                                         const ReleaseArgs rel) {
   pdl_prologue();
+  release_map(rel);
   const int32_t off = ec[0], E = ec[1];
   const int32_t p0 = (blockIdx.x * kBlock + threadIdx.x) * 4;
   if (p0 >= E) return;
@@ -624,35 +668,20 @@ __global__ void __launch_bounds__(kBlock) relabel_kernel(int32_t* __restrict__ a
 #pragma unroll
   for (int k = 0; k < 4; k++) x[k] = (p0 + k < E) ? agg_src[off + p0 + k] : 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) y[k] = (x[k] < 0) ? __ldcg(agg_src + off + ~x[k]) : x[k];
+  for (int k = 0; k < 4; k++)  // L1-cached: first occurrences of hub vertices are read thousands of times
+    y[k] = (x[k] < 0) ? __ldca(agg_src + off + ~x[k]) : x[k];
 #pragma unroll
   for (int k = 0; k < 4; k++)
     if (x[k] < 0) agg_src[off + p0 + k] = y[k];
 }
 
-// ClearPosMap (:542-548): the position-map words of this batch's vertices go back to "not in the batch".
-// O(batch) work; the map itself is O(N) like the reference's, but never memset.
-__global__ void __launch_bounds__(kBlock) pm_clear_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ nc,
-                                                          uint32_t* pm, int32_t l2) {
+// ClearPosMap (:542-548) as its own launch (lg_io_complete of the op-by-op API): the position-map words of this
+// batch's vertices go back to "not in the batch".  O(batch) scatter — the map itself is O(N) like the reference's, but
+// never memset — or, for maps of a few MB and the hashed table, one streaming fill at store bandwidth (products: 9.8 MB
+// against ~0.9 M random 4-byte stores).
+__global__ void __launch_bounds__(kBlock) release_kernel(const ReleaseArgs rel) {
   pdl_prologue();
-  const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
-  int32_t n = nc[LG_INTRABATCH_CON * 2 + 1];
-  const int32_t seeds = nc[LG_INTRABATCH_CON * 3];
-  if (seeds > n) n = seeds;  // before the first hop nc[7] is still 0
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int32_t v = ids[i];
-    if (v >= 0) st_u32_hint(pm + v, kPmEmpty, keep);
-  }
-}
-
-// Streaming release of a whole map: 16-byte stores of all-ones over `n16` uint4 words.  Used for the HASHED table
-// (32 MB per batch) and for small dense maps, where one pass over 4N bytes at store bandwidth beats the O(batch)
-// scatter of pm_clear_kernel (products: 9.8 MB vs ~0.9 M random 4-byte stores).  A kernel rather than a memset node
-// so that the chain stays kernel -> kernel (PDL).
-__global__ void __launch_bounds__(kBlock) map_fill_kernel(uint4* __restrict__ p, int64_t n16) {
-  pdl_prologue();
-  const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) p[i] = ones;
+  release_map(rel);
 }
 
 // HotnessMeasure (cache/cache_impl.cuh:190-198) + max_ids_ (cache/cache.cu:59-61)
@@ -677,7 +706,7 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //   LG_SAMPLE_TILE   frontier entries per CTA of the long hops (32..256)
 //   LG_SAMPLE_MINB   6 (default) = the 256-entry sample kernel of the dense layout is capped at 40 registers so that
 //                    6 CTAs fit an SM: the 782 tiles of a 200 k-entry frontier run as one wave (592 slots otherwise)
-//   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8 or 12; default 12 dense, 8 hashed: one wave)
+//   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8, 12 or 16; default 12 dense, 16 hashed: one wave)
 //   LG_PM_FILL_MB    dense position maps up to this size (default 16 MB) are released by a streaming fill instead of
 //                    the O(batch) scatter
 //   LG_RED_PRECHECK  1 (default) = dense layout: L1-cached look at the map word before the RED.MIN; skips the RED when the
@@ -730,12 +759,12 @@ static int pick_tile_f_tuned(int64_t frontier_max) {
   return (t == 256 && (o == 32 || o == 64 || o == 128 || o == 256)) ? o : t;
 }
 static int pick_rank_items(int64_t edges_max, bool hashed) {
-  // all tiles of a hop resident at once when possible: 4 edges per thread for short hops; for long ones 12 (dense: 46
-  // registers, 5 CTAs per SM, 652 tiles for 2 M edges) or 8 (hashed: 60 registers; 12 would need 80)
+  // all tiles of a hop resident at once: 4 edges per thread for short hops; for long ones 12 (dense: 32 registers,
+  // 652 tiles for 2 M edges) or 16 (hashed: 58 registers, 4 CTAs per SM = 592 slots for 489 tiles)
   if (edges_max <= 4ll * kBlock * kSMs * 5) return 4;
   const int o = sampler_tune().rank_items;
-  if (o == 4 || o == 8 || o == 12) return o;
-  return hashed ? 8 : 12;
+  if (o == 4 || o == 8 || o == 12 || o == 16) return o;
+  return hashed ? 16 : 12;
 }
 
 extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
@@ -942,14 +971,29 @@ extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {
   return map_bytes + 2 * s->slots_per_hop[s->n_hops] * 4 + s->small_bytes + 4;
 }
 
-// the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
-static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
-  if (!s->hashed) {  // HASHED: the table is re-initialised by the next lg_batch_generate instead
-    if (s->num_nodes * 4 <= (int64_t)sampler_tune().pm_fill_mb * (1ll << 20))
-      LG_CUDA(lg_launch_opt(pdl_on(s, 2), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->pm, (s->num_nodes + 3) / 4));
-    else
-      LG_CUDA(lg_launch_opt(pdl_on(s, 2), pm_clear_kernel, kSMs * 4, kBlock, 0, st, (const int32_t*)b->ids,
-                        (const int32_t*)b->node_counter, s->pm, lg_l2_hints()));
+// how the map of this handle is released after batch `b`
+static ReleaseArgs release_args(const lg_sampler* s, const lg_batch* b) {
+  ReleaseArgs r;
+  memset(&r, 0, sizeof(r));
+  r.l2 = lg_l2_hints();
+  if (s->hashed) {  // O(batch)-sized table, L2-resident: one streaming fill instead of an O(batch) random clear
+    r.fill = (uint4*)s->table;
+    r.n16 = ((int64_t)s->table_mask + 1) / 2;
+  } else if (s->num_nodes * 4 <= (int64_t)sampler_tune().pm_fill_mb * (1ll << 20)) {
+    r.fill = (uint4*)s->pm;
+    r.n16 = (s->num_nodes + 3) / 4;
+  } else {
+    r.pm = s->pm;
+    r.ids = b->ids;
+    r.nc = b->node_counter;
+  }
+  return r;
+}
+// bookkeeping after a release was enqueued on `st` (as its own launch or inside the batch's last kernel)
+static int released(lg_sampler* s, cudaStream_t st) {
+  if (s->hashed) {
+    s->table_clean = 1;
+  } else {
     // the next batch's inserts must not overtake this release when the host enqueues them on another stream
     LG_CUDA(cudaEventRecord(s->ev_clear, st));
     s->clear_stream = st;
@@ -957,6 +1001,16 @@ static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b)
   }
   s->pm_dirty = 0;
   return 0;
+}
+// the position-map words of the batch last generated into `b` go back to "absent" (ClearPosMap, :542-548)
+static int clear_position_map(lg_sampler* s, cudaStream_t st, const lg_batch* b) {
+  if (!s->pm_dirty) return 0;  // already released by the batch's last kernel (lg_run_batch)
+  if (s->hashed) {  // the table is re-initialised by the next lg_batch_generate instead
+    s->pm_dirty = 0;
+    return 0;
+  }
+  LG_CUDA(lg_launch_opt(pdl_on(s, 2), release_kernel, kSMs * 8, kBlock, 0, st, release_args(s, b)));
+  return released(s, st);
 }
 static DedupMap map_of(const lg_sampler* s) {
   DedupMap m;
@@ -980,8 +1034,9 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
     if (rc) return rc;
   }
   if (s->clear_recorded && s->clear_stream != st) LG_CUDA(cudaStreamWaitEvent(st, s->ev_clear, 0));
-  if (s->hashed)  // O(batch)-sized table, L2-resident: one streaming fill instead of an O(batch) random clear
-    LG_CUDA(lg_launch_opt(pdl_on(s, 4), map_fill_kernel, kSMs * 8, kBlock, 0, st, (uint4*)s->table, ((int64_t)s->table_mask + 1) / 2));
+  if (s->hashed && !s->table_clean)  // not already re-initialised by the previous batch's last kernel
+    LG_CUDA(lg_launch_opt(pdl_on(s, 4), release_kernel, kSMs * 8, kBlock, 0, st, release_args(s, b)));
+  s->table_clean = 0;
   long long done = (long long)batch_size * ((long long)counter + 1);
   int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
   if (size < 0) size = 0;
@@ -1021,6 +1076,7 @@ static cudaError_t launch_sample(bool pdl, int tile_f, int grid, cudaStream_t st
 template <bool HASHED, bool PUBLISH>
 static cudaError_t launch_rank(bool pdl, int items, int grid, cudaStream_t st, const RankArgs& r) {
   switch (items) {
+    case 16: return lg_launch_opt(pdl, rank_kernel<16, HASHED, PUBLISH>, grid, kBlock, 0, st, r);
     case 12: return lg_launch_opt(pdl, rank_kernel<12, HASHED, PUBLISH>, grid, kBlock, 0, st, r);
     case 8: return lg_launch_opt(pdl, rank_kernel<8, HASHED, PUBLISH>, grid, kBlock, 0, st, r);
     default: return lg_launch_opt(pdl, rank_kernel<4, HASHED, PUBLISH>, grid, kBlock, 0, st, r);
@@ -1030,7 +1086,7 @@ static cudaError_t launch_rank(bool pdl, int items, int grid, cudaStream_t st, c
 // one hop: sample + rank (+ the hop's own relabel pass unless the caller folds it into the next hop's sample kernel)
 static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, int32_t hop, int32_t rng_kind,
                       uint64_t rng_seed, uint32_t batch_id, uint32_t stream_id, const lg_batch* b,
-                      unsigned long long* edge_hotness, bool relabel_prev, bool relabel_own) {
+                      unsigned long long* edge_hotness, bool relabel_prev, bool relabel_own, bool release) {
   const int h = hop - 1;
   if (s->hashed) {  // every hop relabels itself; the next hop reads agg_src instead of the table
     relabel_prev = false;
@@ -1094,7 +1150,14 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   }
   if (relabel_own) {
     const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
-    LG_CUDA(lg_launch_opt(pdl_on(s), relabel_kernel, (int)grid, kBlock, 0, st, b->agg_src, (const int32_t*)b->edge_counter));
+    ReleaseArgs rel;
+    memset(&rel, 0, sizeof(rel));
+    if (release) rel = release_args(s, b);
+    LG_CUDA(lg_launch_opt(pdl_on(s), relabel_kernel, (int)grid, kBlock, 0, st, b->agg_src, (const int32_t*)b->edge_counter, rel));
+    if (release) {
+      int rc = released(s, st);
+      if (rc) return rc;
+    }
   }
   return 0;
 }
@@ -1111,7 +1174,7 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   LG_REQUIRE(topo->num_nodes <= s->num_nodes, "lg_random_sample: topology has %lld vertices, sampler was created for %lld",
              (long long)topo->num_nodes, (long long)s->num_nodes);
   return sample_hop(s, (cudaStream_t)stream_, topo, hop, rng_kind, rng_seed, batch_id, stream_id, b, edge_hotness,
-                    /*relabel_prev=*/false, /*relabel_own=*/true);
+                    /*relabel_prev=*/false, /*relabel_own=*/true, /*release=*/false);
 }
 
 extern "C" int lg_io_submit(lg_sampler*, lg_stream_t, int32_t, const lg_batch*) { return 0; }
@@ -1161,7 +1224,7 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
     if (hop > 0) {
       // the relabel pass of hop h rides in the sample kernel of hop h+1; only the last hop runs its own
       rc = sample_hop(s, main_st, topo, hop, p->rng_kind, p->rng_seed, p->batch_id, p->stream_id, b, nullptr,
-                      /*relabel_prev=*/hop > 1, /*relabel_own=*/hop == s->n_hops);
+                      /*relabel_prev=*/hop > 1, /*relabel_own=*/hop == s->n_hops, /*release=*/hop == s->n_hops);
       if (rc) return rc;
     }
     if (!cache) continue;

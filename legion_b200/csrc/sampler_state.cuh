@@ -29,6 +29,7 @@ struct lg_sampler {
   cudaEvent_t ev_clear;        // recorded after the last release of the position map (lg_io_complete may run on
   cudaStream_t clear_stream;   // another stream than the next lg_batch_generate: engine/server.cu puts it on stream 2)
   int32_t clear_recorded;
+  int32_t table_clean;         // HASHED: the table was re-initialised by the previous batch's last kernel
   int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)
   uint8_t* small;        // memset-per-batch region: HopState[hops] + chained-scan tile states
   int64_t small_bytes;

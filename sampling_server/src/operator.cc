@@ -3,6 +3,8 @@
 // params->event.
 #include "operator.h"
 
+#include <cstdlib>
+
 #include "cache.h"
 #include "ipc_service.h"
 #include "memorypool.h"
@@ -52,15 +54,28 @@ class RandomSampleOP : public Operator {
   int op_id_;
 };
 
+// The reference gathers after every sampling op (seeds, hop 1, ..., hop H: H+1 launches per batch).  By default the
+// lookup ops before the last one only record their event and the last one gathers the rows of all hops in one launch
+// (lg_feature_cache_lookup_range): the trainer sees the same buffers and the same final counters, and every launch
+// less matters next to the streaming gather.  LEGION_FUSE_GATHERS=0 restores one gather per op.
 class CacheLookupOP : public Operator {
  public:
   explicit CacheLookupOP(int op_id) : op_id_(op_id) {}
   void run(OpParams* params) override {
+    static const bool fuse = [] {
+      const char* e = std::getenv("LEGION_FUSE_GATHERS");
+      return !e || std::atoi(e) != 0;
+    }();
     auto* pool = (MemoryPool*)params->memorypool;
     auto* cache = (UnifiedCache*)params->cache;
     int32_t dev = params->device_id;
-    LGCHECK(lg_feature_cache_lookup(pool->sampler, params->stream, cache->FeatureCache(dev), op_id_, cache->LocalPart(dev),
-                                    pool->Batch(), cache->TierRows(dev)));
+    const bool last = op_id_ / INTRABATCH_CON == params->hop_num;
+    if (!fuse)
+      LGCHECK(lg_feature_cache_lookup(pool->sampler, params->stream, cache->FeatureCache(dev), op_id_, cache->LocalPart(dev),
+                                      pool->Batch(), cache->TierRows(dev)));
+    else if (last)
+      LGCHECK(lg_feature_cache_lookup_range(pool->sampler, params->stream, cache->FeatureCache(dev), op_id_, 0,
+                                            cache->LocalPart(dev), pool->Batch(), cache->TierRows(dev)));
     LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:

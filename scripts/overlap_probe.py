@@ -89,8 +89,8 @@ def dram_stream(k):
 def random_reads(k):
     with torch.cuda.stream(S3):
         for _ in range(k * 2): big[idx]
-for name, fn in (("bf16 matmul 4096^3", matmul), ("L2-resident elementwise", l2_elementwise), ("DRAM streaming 256 MB/iter", dram_stream),
-                 ("2x2M random 4-byte reads/iter", random_reads)):
+for name, fn in (() if os.environ.get("PROBE") == "tiny" else (("bf16 matmul 4096^3", matmul), ("L2-resident elementwise", l2_elementwise), ("DRAM streaming 256 MB/iter", dram_stream),
+                 ("2x2M random 4-byte reads/iter", random_reads))):
     fn(3); torch.cuda.synchronize()
     print(name.ljust(32), "alone", timed([("other", S3, fn)]), "with gather", timed([("other", S3, fn), ("gather", S2, gather)]))
 
@@ -101,9 +101,10 @@ for ctas, thr in ((1, 32), (148, 32), (148 * 4, 256), (148 * 8, 256)):
             capi.check(dp.L.lg_debug_spin(C.c_void_p(S3.cuda_stream), ctas, thr, 250000))   # ~0.13 ms at 1.9 GHz
     spin(3); torch.cuda.synchronize()
     print(f"spin {ctas}x{thr}".ljust(32), "alone", timed([("other", S3, spin)]), "with gather", timed([("other", S3, spin), ("gather", S2, gather)]))
-# many short launches of an empty-ish kernel
-def tiny(k):
-    for _ in range(k * 27):
-        capi.check(dp.L.lg_debug_spin(C.c_void_p(S3.cuda_stream), 148, 128, 2000))
-tiny(3); torch.cuda.synchronize()
-print("27 tiny launches/iter".ljust(32), "alone", timed([("other", S3, tiny)]), "with gather", timed([("other", S3, tiny), ("gather", S2, gather)]))
+# many short launches of an empty-ish kernel: is the disturbance per SM (only where the CTAs land) or global?
+for ctas, thr, per_iter in ((148, 128, 27), (1, 128, 27), (16, 128, 27), (148, 128, 7), (148 * 4, 256, 7)):
+    def tiny(k, ctas=ctas, thr=thr, per_iter=per_iter):
+        for _ in range(k * per_iter):
+            capi.check(dp.L.lg_debug_spin(C.c_void_p(S3.cuda_stream), ctas, thr, 2000))
+    tiny(3); torch.cuda.synchronize()
+    print(f"{per_iter} tiny launches/iter {ctas}x{thr}".ljust(32), "alone", timed([("other", S3, tiny)]), "with gather", timed([("other", S3, tiny), ("gather", S2, gather)]))
