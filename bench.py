@@ -512,11 +512,12 @@ def run_ours(args):
             "tier_rows": {"local": int(tiers[0]), "peer": int(tiers[1]), "host_or_backing": int(tiers[2])},
             "clocks": clk,
         }
-        # batch_generate + (sample, rank) per hop + the last hop's relabel + pm_clear + gathers (memsets/copies not counted)
-        if dp.L.lg_sampler_dedup_layout(dp.sampler) == 1:  # hashed: + seed ids, a relabel per hop, no clear pass
+        # lg_run_batch: batch_generate + (sample, rank) per hop + the last hop's relabel (which also releases the
+        # position map) + gathers; no memset nodes
+        if dp.L.lg_sampler_dedup_layout(dp.sampler) == 1:  # hashed: + seed ids, a relabel per hop
             out["gpu_launches"] = args.steps * (2 + 3 * H + n_gather_launches)
         else:
-            out["gpu_launches"] = args.steps * (1 + 2 * H + 1 + 1 + n_gather_launches)
+            out["gpu_launches"] = args.steps * (1 + 2 * H + 1 + n_gather_launches)
         tr = recorded_traffic()
         if tr:
             out["roofline"]["traffic"] = tr.get("traffic_bytes_per_step")

@@ -416,11 +416,15 @@ extern "C" int lg_device_mem_info(int64_t* free_bytes, int64_t* total_bytes) {
 // diagnostics: a kernel that only spins (no memory traffic) — scripts/overlap_probe.py uses it to tell SM-side
 // contention from memory-side contention next to the gather
 __global__ void lg_spin_kernel(long long cycles, int* sink) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long t0 = clock64();
   int x = threadIdx.x;
   while (clock64() - t0 < cycles) x = x * 1664525 + 1013904223;
   if (x == 0x7fffffff && sink) *sink = x;
 }
+// LG_SPIN_PDL=1: the spinner is launched with programmatic stream serialization (probe: does a PDL launch disturb the
+// gather less than a plain one?)
 extern "C" int lg_debug_spin(lg_stream_t stream, int32_t ctas, int32_t threads, int64_t cycles) {
   static int carve = [] {
     const char* e = getenv("LG_SPIN_CARVEOUT");
@@ -429,7 +433,10 @@ extern "C" int lg_debug_spin(lg_stream_t stream, int32_t ctas, int32_t threads, 
     return v;
   }();
   (void)carve;
-  lg_spin_kernel<<<ctas, threads, 0, (cudaStream_t)stream>>>((long long)cycles, nullptr);
-  LG_LAUNCH_OK();
+  static const bool pdl = [] {
+    const char* e = getenv("LG_SPIN_PDL");
+    return e && atoi(e) != 0;
+  }();
+  LG_CUDA(lg_launch_opt(pdl, lg_spin_kernel, ctas, threads, 0, (cudaStream_t)stream, (long long)cycles, (int*)nullptr));
   return 0;
 }

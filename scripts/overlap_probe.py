@@ -101,6 +101,21 @@ for ctas, thr in ((1, 32), (148, 32), (148 * 4, 256), (148 * 8, 256)):
             capi.check(dp.L.lg_debug_spin(C.c_void_p(S3.cuda_stream), ctas, thr, 250000))   # ~0.13 ms at 1.9 GHz
     spin(3); torch.cuda.synchronize()
     print(f"spin {ctas}x{thr}".ljust(32), "alone", timed([("other", S3, spin)]), "with gather", timed([("other", S3, spin), ("gather", S2, gather)]))
+# the same launches spread over independent streams: is it the launch, or the completion -> launch dependency?
+many = [torch.cuda.Stream() for _ in range(9)]
+def tiny_streams(k):
+    for i in range(k * 27):
+        capi.check(dp.L.lg_debug_spin(C.c_void_p(many[i % len(many)].cuda_stream), 1, 128, 2000))
+def timed_many(fn):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(S2): a.record()
+    fn(n); gather(n)
+    with torch.cuda.stream(S2): b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+tiny_streams(3); torch.cuda.synchronize()
+print("27 tiny launches/iter over 9 independent streams: gather", timed_many(tiny_streams))
 # many short launches of an empty-ish kernel: is the disturbance per SM (only where the CTAs land) or global?
 for ctas, thr, per_iter in ((148, 128, 27), (1, 128, 27), (16, 128, 27), (148, 128, 7), (148 * 4, 256, 7)):
     def tiny(k, ctas=ctas, thr=thr, per_iter=per_iter):

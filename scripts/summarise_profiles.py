@@ -26,7 +26,7 @@ for r in rows_of(launches):
     a[1] += us
 ours = {k: v for k, v in agg.items() if "<unnamed>" in k or "lg::" in k}
 step = {k: v for k, v in ours.items() if any(s in k for s in ("gather_", "sample_hop", "rank_kernel", "relabel_kernel",
-                                                                  "batch_generate", "pm_clear"))}
+                                                                  "batch_generate", "release_kernel", "seed_local"))}
 tot = sum(v[1] for v in step.values()) or 1.0
 with open(f"profiles/{tag}_launches_summary.md", "w") as f:
     f.write(f"# {tag} — launch list (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n`{cmd}`; "
