@@ -24,6 +24,8 @@ hot = torch.bincount(ix.long(), minlength=N)
 order, _ = dp.rank_hotness(hot)
 dp.build_feature_cache(order, N)
 dp.set_overlap(0); dp.set_gather_fusion(2)
+if os.environ.get("PROBE_GATHER") == "ldg":
+    dp.set_gather_variant(capi.GATHER_LDG)
 bg = dp.alloc_batch()            # prepared batch for the gather-only stream
 dp.run_once(dp.params(d_train, d_lab, B, 0, seed=1, batch_id=0), bg); torch.cuda.synchronize()
 rows = int(bg.node_counter[9 + H].item())
