@@ -489,7 +489,7 @@ def run_ours(args):
                                 + (f", hottest {args.cache_ratio:.3f} of the rows in HBM ({cap} rows/GPU), the rest in pinned host memory (UVA)" if feat_host else ", fully HBM-cached")
                                 + (f"; topology in pinned host memory (UVA) with the hottest {args.topo_cache_ratio:.3f} of the adjacency lists cached in HBM ({topo_cap} rows/GPU)" if topo_host else "; topology replicated in HBM"),
                        "feature_cache_ratio": args.cache_ratio, "topology": args.topo, "topology_cache_ratio": args.topo_cache_ratio if topo_host else None,
-                       "rng": "philox4x32-10", "position_map": ["dense u32[N]", "hashed L2-resident table"][dp.L.lg_sampler_dedup_layout(dp.sampler)], "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined over the 2 INTERBATCH_CON slots (gather of batch k overlaps sampling of batch k+1)"][args.overlap],
+                       "rng": "philox4x32-10", "position_map": ["dense u32[N]", "hashed L2-resident table"][dp.L.lg_sampler_dedup_layout(dp.sampler)], "gather_mover": args.gather, "gather_fusion": args.fuse, "batches_in_flight": args.inflight, "schedule": ["one stream", "gather overlaps next hop, joined per batch", "pipelined: every in-flight runner owns 2 INTERBATCH_CON buffer slots; the gather of batch k overlaps the sampling of the following batches"][args.overlap],
                        "l2": "working set (topology + features + per-batch output, >1.5 GB) exceeds the 126 MB L2; every step samples different seeds"},
             "e2e": {"value": seeds / t_e2e, "unit": "seeds/s", "h2d_bytes_per_step": 2 * 4 * B, "d2h_bytes_per_step": 128,
                     "note": "every step: seed ids+labels copied from pinned host memory (H2D), lg_run_batch_host_async, both counter "
@@ -514,8 +514,8 @@ def run_ours(args):
         }
         # lg_run_batch: batch_generate + (sample, rank) per hop + the last hop's relabel (which also releases the
         # position map) + gathers; no memset nodes
-        if dp.L.lg_sampler_dedup_layout(dp.sampler) == 1:  # hashed: + seed ids, a relabel per hop
-            out["gpu_launches"] = args.steps * (2 + 3 * H + n_gather_launches)
+        if dp.L.lg_sampler_dedup_layout(dp.sampler) == 1:  # hashed: + the seeds' local ids
+            out["gpu_launches"] = args.steps * (2 + 2 * H + 1 + n_gather_launches)
         else:
             out["gpu_launches"] = args.steps * (1 + 2 * H + 1 + n_gather_launches)
         tr = recorded_traffic()
@@ -638,7 +638,7 @@ def main():
                     help="where the full CSR lives: replicated in HBM, or pinned host memory read through UVA")
     ap.add_argument("--topo-cache-ratio", type=float, default=0.0,
                     help="with --topo host: fraction of the vertices whose adjacency lists are cached in HBM")
-    ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (own scratch + stream each)")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight per GPU (own scratch + stream each); 3 measured best: host-fed e2e 36.3 -> 40.4 M seeds/s")
     ap.add_argument("--overlap", type=int, default=2, choices=[0, 1, 2],
                     help="0 one stream; 1 gathers overlap the next hop; 2 pipelined across the two batch slots")
     ap.add_argument("--cpu-steps", type=int, default=20)

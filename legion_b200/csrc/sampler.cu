@@ -34,6 +34,8 @@
 #include "common.cuh"
 #include "sampler_state.cuh"
 
+#include <mutex>
+
 using namespace lg;
 
 namespace {
@@ -201,37 +203,50 @@ __device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* s_re
 // ------------------------------------------------------------------------------------------
 // batch_generate + op-0 counter_update (engine/operator_impl.cu:27-89,159-165)
 // ------------------------------------------------------------------------------------------
+struct BatchGenArgs {
+  const int32_t* all_ids;
+  const int32_t* all_labels;
+  int32_t total_cap, size, counter, hop_num;
+  int32_t* ids;
+  int32_t* labels;
+  int32_t* nc;
+  int32_t* ec;
+  DedupMap map;
+  u64* small;  // per-batch scan state (tickets + tile words), zeroed here
+  int32_t small_words;
+  int32_t l2;
+};
+// One pass over the launch's threads (t = global thread index of n_threads): works for any grid size.
 template <bool HASHED>
-__global__ void __launch_bounds__(kBlock) batch_generate_kernel(
-    const int32_t* __restrict__ all_ids, const int32_t* __restrict__ all_labels, int32_t total_cap,
-    int32_t size, int32_t counter, int32_t hop_num, int32_t* __restrict__ ids, int32_t* __restrict__ labels,
-    int32_t* __restrict__ nc, int32_t* __restrict__ ec, const DedupMap map, u64* __restrict__ small,
-    int32_t small_words, int32_t l2) {
-  pdl_prologue();
-  const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
-  int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  // reset of the per-batch scan state (tickets + tile aggregates), a few KB: done here instead of a memset node so
-  // that the whole chain is kernel -> kernel (the reference memsets an N/8-byte bitmap at this point, :151)
-  for (int32_t i = idx; i < small_words; i += gridDim.x * blockDim.x) small[i] = 0ull;
-  if (blockIdx.x == 0 && threadIdx.x < LG_COUNTER_SLOTS) {
-    int t = threadIdx.x;
+__device__ __forceinline__ void batch_generate_body(const BatchGenArgs& g, int32_t t, int32_t n_threads) {
+  const u64 keep = l2_policy((g.l2 & 4) ? 1 : 0);
+  // reset of the per-batch scan state, a few KB: done here instead of a memset node so that the whole chain is
+  // kernel -> kernel (the reference memsets an N/8-byte bitmap at this point, :151)
+  for (int32_t i = t; i < g.small_words; i += n_threads) g.small[i] = 0ull;
+  if (t < LG_COUNTER_SLOTS) {
     int32_t v = 0;
-    if (t == 1 || t == LG_INTRABATCH_CON * 3) v = size;  // nc[1], nc[9]
-    if (t == LG_INTRABATCH_CON * 3 - 1) v = hop_num;     // nc[8]
-    nc[t] = v;
-    ec[t] = 0;
+    if (t == 1 || t == LG_INTRABATCH_CON * 3) v = g.size;  // nc[1], nc[9]
+    if (t == LG_INTRABATCH_CON * 3 - 1) v = g.hop_num;     // nc[8]
+    g.nc[t] = v;
+    g.ec[t] = 0;
   }
-  if (idx >= size) return;
-  long long pos = (long long)size * counter + idx;  // the reference strides by the clipped size (:40,:44,:162)
-  if (pos >= total_cap) {
-    ids[idx] = -1;
-    labels[idx] = -1;
-    return;
+  for (int32_t idx = t; idx < g.size; idx += n_threads) {
+    const long long pos = (long long)g.size * g.counter + idx;  // the reference strides by the clipped size (:40,:44,:162)
+    if (pos >= g.total_cap) {
+      g.ids[idx] = -1;
+      g.labels[idx] = -1;
+      continue;
+    }
+    const int32_t v = g.all_ids[pos % g.total_cap];
+    g.ids[idx] = v;
+    g.labels[idx] = g.all_labels[pos % g.total_cap];
+    if (v >= 0) map_insert_min<HASHED>(g.map, (uint32_t)v, (uint32_t)idx, keep);  // position_map (:51): local index = first position
   }
-  int32_t v = all_ids[pos % total_cap];
-  ids[idx] = v;
-  labels[idx] = all_labels[pos % total_cap];
-  if (v >= 0) map_insert_min<HASHED>(map, (uint32_t)v, (uint32_t)idx, keep);  // position_map (:51): local index = first position
+}
+template <bool HASHED>
+__global__ void __launch_bounds__(kBlock) batch_generate_kernel(const BatchGenArgs g) {
+  pdl_prologue();
+  batch_generate_body<HASHED>(g, (int32_t)(blockIdx.x * blockDim.x + threadIdx.x), (int32_t)(gridDim.x * blockDim.x));
 }
 
 // HASHED only: batch-local id of every seed (= its first position; duplicates share it).  The hashed insert moves
@@ -251,29 +266,32 @@ __global__ void __launch_bounds__(kBlock) seed_local_kernel(const int32_t* __res
 // ------------------------------------------------------------------------------------------
 // sample_hop_kernel
 // ------------------------------------------------------------------------------------------
+struct SampleHop {  // what changes from hop to hop
+  const int32_t* frontier_prev;  // hop > 1: global ids of the previous hop's sampled sources
+  int32_t* gid_out;              // this hop's sampled sources (global ids), hop-relative positions
+  u64* tile_state;
+  u64* anchors;                  // group words of the tile prefix
+  HopState* hs;
+  int32_t hop;
+  int32_t fanout;
+  uint32_t fanout_magic;  // ceil(2^32 / fanout): slot / fanout as one multiply-high (slot < 2^16)
+  int32_t relabel_prev;   // also write the previous hop's agg_src (its construct_graph) from the position map
+};
 struct SampleArgs {
   lg_topology topo;
-  const int32_t* frontier_prev;  // hop > 1: global ids of the previous hop's sampled sources
   const int32_t* seed_local;     // HASHED: batch-local ids of the seeds (seed_local_kernel)
-  int32_t* gid_out;              // this hop's sampled sources (global ids), hop-relative positions
   int32_t* ids;
   int32_t* agg_src;
   int32_t* agg_dst;
   int32_t* nc;
   int32_t* ec;
   DedupMap map;
-  u64* tile_state;
-  u64* anchors;
-  HopState* hs;
   u64* edge_hot;
-  int32_t hop;
-  int32_t fanout;
-  uint32_t fanout_magic;  // ceil(2^32 / fanout): slot / fanout as one multiply-high (slot < 2^16)
-  int32_t relabel_prev;   // also write the previous hop's agg_src (its construct_graph) from the position map
   int32_t precheck;       // DENSE: L1-cached look at the map word before the RED.MIN (LG_RED_PRECHECK)
   uint32_t batch_id, stream_id, k0, k1;
   int32_t l2;  // lg_l2_hints()
   u64* trace;
+  SampleHop h;
 };
 
 // Row of vertex v: (part, first edge, degree) through the topology directory (FindTopo, cache/cache.cu:217-225)
@@ -286,57 +304,69 @@ __device__ __forceinline__ void row_locate(const lg_topology& t, int32_t v, int3
   }
 }
 
-template <int TILE_F, int RNG, bool HASHED, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleArgs a) {
+template <int TILE_F>
+struct SampleSmem {
+  long long start[TILE_F];
+  const int32_t* indices[TILE_F];
+  int32_t deg[TILE_F];
+  int32_t cnt[TILE_F];
+  int32_t off[TILE_F];
+  int32_t flocal[TILE_F];
+  int32_t red[kBlock / 32];
+};
+
+// One tile of TILE_F frontier entries, by the whole CTA.  Returns false when `tile` is past the hop's last tile.
+template <int TILE_F, int RNG, bool HASHED>
+__device__ __forceinline__ bool sample_tile(const SampleArgs& a, const SampleHop& h, const int tile, SampleSmem<TILE_F>& sm) {
   static_assert(TILE_F <= kBlock, "one thread per frontier entry of the tile");
-  __shared__ long long s_start[TILE_F];
-  __shared__ const int32_t* s_indices[TILE_F];
-  __shared__ int32_t s_deg[TILE_F];
-  __shared__ int32_t s_cnt[TILE_F];
-  __shared__ int32_t s_off[TILE_F];
-  __shared__ int32_t s_flocal[TILE_F];
-  __shared__ int32_t s_red[kBlock / 32];
-  __shared__ int32_t s_tile;
+  long long* const s_start = sm.start;
+  const int32_t** const s_indices = sm.indices;
+  int32_t* const s_deg = sm.deg;
+  int32_t* const s_cnt = sm.cnt;
+  int32_t* const s_off = sm.off;
+  int32_t* const s_flocal = sm.flocal;
+  int32_t* const s_red = sm.red;
 
   constexpr int U = HASHED ? kSlotUnrollHashed : kSlotUnroll;  // slots in flight per thread
   const int tid = threadIdx.x;
-  pdl_prologue();
-  if (tid == 0) s_tile = atomicAdd(&a.hs->sample_ticket, 1);
   const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0), once = l2_policy((a.l2 & 8) ? 2 : 0);
-  const bool first_hop = (a.hop == 1);
+  const bool first_hop = (h.hop == 1);
   const int32_t F = first_hop ? a.nc[1] : a.ec[1];          // :201-206
   const int32_t prev_edge_off = a.ec[0];
   const int32_t edge_base = a.ec[0] + a.ec[1];              // :275
-  __syncthreads();
-  const int tile = s_tile;
-  const int tslot = (a.hop - 1) * 2;
+  const int tslot = (h.hop - 1) * 2;
   if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
   const int n_tiles = (F + TILE_F - 1) / TILE_F;
   if (tile >= n_tiles) {
     if (n_tiles == 0 && tile == 0 && tid == 0) a.ec[2] = 0;
-    return;
+    return false;
   }
-  const int32_t c = a.fanout;
+  const int32_t c = h.fanout;
   const int32_t i0 = tile * TILE_F;
 
   // 1. row lookup for the tile's frontier entries
   int32_t cnt = 0, fl = 0;
-  bool live = false;
+  bool live = false, patched = false;
   if (tid < TILE_F) {
     const int32_t i = i0 + tid;
     int32_t deg = 0;
     long long start = 0;
     const int32_t* ind = a.topo.indices[a.topo.n_parts];
     if (i < F) {
-      const int32_t v = first_hop ? a.ids[i] : a.frontier_prev[i];
+      const int32_t v = first_hop ? a.ids[i] : h.frontier_prev[i];
       if (v >= 0) {
         live = true;
         // batch-local index of the frontier vertex (position_map, :291-294): final since the previous op.  The load
         // is issued here and consumed after the prefix (s_flocal).
-        if (HASHED)  // never from the table while this launch inserts (see seed_local_kernel)
+        if (HASHED) {  // never from the table while this launch inserts (see seed_local_kernel)
           fl = first_hop ? a.seed_local[i] : a.agg_src[prev_edge_off + i];
-        else
+          if (fl < 0) {  // the previous hop's rank pass left ~p_first: the first occurrence's entry holds the id
+            fl = a.agg_src[prev_edge_off + ~fl];  // (construct_graph of the previous hop, second half, fused)
+            patched = true;
+          }
+        } else {
           fl = (int32_t)map_lookup<false>(a.map, (uint32_t)v, keep);
+        }
         int part;
         long long row;
         row_locate(a.topo, v, a.topo.directory ? ld_nc_s32_hint(a.topo.directory + v, keep) : -1, &part, &row);
@@ -360,11 +390,12 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
   int32_t total;
   const int32_t off = block_exclusive_scan(cnt, s_red, &total);
   if (tid < TILE_F) s_off[tid] = off;
-  const int32_t base = block_exclusive_prefix(a.tile_state, a.anchors, tile, total, s_red);
+  const int32_t base = block_exclusive_prefix(h.tile_state, h.anchors, tile, total, s_red);
   if (tid == 0 && tile == n_tiles - 1) a.ec[2] = base + total;  // E_h (:264)
   if (tid < TILE_F) {
     s_flocal[tid] = fl;
-    if (!HASHED && a.relabel_prev && live) a.agg_src[prev_edge_off + i0 + tid] = fl;  // construct_graph of the previous hop, fused
+    // construct_graph of the previous hop, fused: every entry (dense), or the ~p_first entries (hashed)
+    if (HASHED ? patched : (h.relabel_prev && live)) a.agg_src[prev_edge_off + i0 + tid] = fl;
   }
   __syncthreads();
   if (tid == 0) trace_mark(a.trace, tslot, tile, 2);
@@ -380,12 +411,12 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
       const int k = k0 + u * kBlock;
       p[u] = -1;
       if (k < n_slots) {
-        const int t = (c == 1) ? k : (int)__umulhi((uint32_t)k, a.fanout_magic);
+        const int t = (c == 1) ? k : (int)__umulhi((uint32_t)k, h.fanout_magic);
         const int j = k - t * c;
         if (j < s_cnt[t]) {  // :232  neighbor_offset >= col_size -> none
           const uint32_t slot = (uint32_t)(i0 + t) * (uint32_t)c + (uint32_t)j;
           const int32_t pick =
-              pick_neighbor<RNG>(slot, s_deg[t], (uint32_t)a.hop, a.batch_id, a.stream_id, a.k0, a.k1);
+              pick_neighbor<RNG>(slot, s_deg[t], (uint32_t)h.hop, a.batch_id, a.stream_id, a.k0, a.k1);
           w[u] = ld_nc_s32_hint(s_indices[t] + s_start[t] + pick, once);  // :240-242
           p[u] = base + s_off[t] + j;
           fl[u] = s_flocal[t];
@@ -398,7 +429,7 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (p[u] >= 0) {
-          a.gid_out[p[u]] = w[u];
+          h.gid_out[p[u]] = w[u];
           a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
           sl[u] = map_home(a.map, (uint32_t)w[u]);
           carry[u] = map_pack((uint32_t)w[u], kNewBit | (uint32_t)p[u]);
@@ -453,7 +484,7 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (p[u] >= 0) {
-          a.gid_out[p[u]] = w[u];
+          h.gid_out[p[u]] = w[u];
           a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
           const uint32_t val = kNewBit | (uint32_t)p[u];
           if (cur[u] > val) red_min_u32_hint(a.map.pm + w[u], val, keep);
@@ -463,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (p[u] >= 0) {
-          a.gid_out[p[u]] = w[u];
+          h.gid_out[p[u]] = w[u];
           a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
           red_min_u32_hint(a.map.pm + w[u], kNewBit | (uint32_t)p[u], keep);
         }
@@ -475,26 +506,40 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
     __syncthreads();
     if (tid == 0) trace_mark(a.trace, tslot, tile, 4);  // whole CTA done
   }
+  return true;
+}
+
+template <int TILE_F, int RNG, bool HASHED, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleArgs a) {
+  __shared__ SampleSmem<TILE_F> sm;
+  __shared__ int32_t s_tile;
+  pdl_prologue();
+  if (threadIdx.x == 0) s_tile = atomicAdd(&a.h.hs->sample_ticket, 1);  // tiles are claimed in order (see block_exclusive_prefix)
+  __syncthreads();
+  sample_tile<TILE_F, RNG, HASHED>(a, a.h, s_tile, sm);
 }
 
 // ------------------------------------------------------------------------------------------
 // rank_kernel: first-occurrence flags -> scan -> batch-local ids in first-seen order, `ids` append, publish
 // ------------------------------------------------------------------------------------------
-struct RankArgs {
+struct RankHop {  // what changes from hop to hop
   const int32_t* gid;  // this hop's sampled sources
-  int32_t* ids;
-  int32_t* nc;
-  int32_t* ec;
-  DedupMap map;
   u64* tile_state;
   u64* anchors;
   HopState* hs;
   int32_t* agg_src;  // non-null: also write this hop's agg_src (construct_graph) as far as this pass knows it
   int32_t hop;
+};
+struct RankArgs {
+  int32_t* ids;
+  int32_t* nc;
+  int32_t* ec;
+  DedupMap map;
   int32_t ids_cap;
   int32_t l2;
   int32_t* status;
   u64* trace;
+  RankHop h;
 };
 
 // PUBLISH: write the final local ids back into the map — needed while a later hop will insert into it (its RED.MIN
@@ -503,26 +548,21 @@ struct RankArgs {
 // batch before this hop (the map word IS its local id), or this edge is the source's first occurrence (it gets the id
 // assigned below).  A later occurrence of a vertex that is new in this hop only knows the position p_first of the first
 // one: it stores ~p_first, and relabel_kernel replaces it by agg_src[p_first] once every tile is done.
+// One tile of kBlock * ITEMS edges, by the whole CTA.  Returns false when `tile` is past the hop's last tile.
 template <int ITEMS, bool HASHED, bool PUBLISH>
-__global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
+__device__ __forceinline__ bool rank_tile(const RankArgs& a, const RankHop& h, const int tile, int32_t* s_red) {
   static_assert(ITEMS % 4 == 0, "edges are loaded as int4");
   constexpr int TILE = kBlock * ITEMS;
-  __shared__ int32_t s_red[kBlock / 32];
-  __shared__ int32_t s_tile, s_last;
   const int tid = threadIdx.x;
-  pdl_prologue();
   const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0);
-  if (tid == 0) s_tile = atomicAdd(&a.hs->rank_ticket, 1);
   const int32_t E = a.ec[2];
   const int32_t node_base = a.nc[0] + a.nc[1];  // :268
-  const int32_t edge_base = a.ec[0] + a.ec[1];  // :275 (the counters move on when the last CTA is done)
-  __syncthreads();
-  const int tile = s_tile;
-  const int tslot = (a.hop - 1) * 2 + 1;
+  const int32_t edge_base = a.ec[0] + a.ec[1];  // :275 (the counters move on when every tile is done)
+  const int tslot = (h.hop - 1) * 2 + 1;
   if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
   const int n_tiles = (E + TILE - 1) / TILE;
-
-  if (tile < n_tiles) {
+  if (tile >= n_tiles) return false;
+  {
     const int32_t p0 = tile * TILE + tid * ITEMS;  // ITEMS consecutive edges per thread
     // The edges are looked up in chunks of CH (all probes of a chunk in flight together) and only a bit per edge
     // survives the chunk.  HASHED: chunks of 8 — with the vertices, 64-bit table words and slots of all ITEMS edges
@@ -536,7 +576,7 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
       uint32_t q[CH];
 #pragma unroll
       for (int k = 0; k < CH; k += 4) {  // the buffer is padded to a multiple of TILE, reads past E are discarded
-        const int4 v = *reinterpret_cast<const int4*>(a.gid + p0 + c + k);
+        const int4 v = *reinterpret_cast<const int4*>(h.gid + p0 + c + k);
         w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
       }
       // L1-cached: a line fetched before the owner publishes holds kNewBit|p_first, one fetched after holds the
@@ -561,8 +601,8 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
         const int32_t p = p0 + c + k;
         if (p < E) {
           if (q[k] == (kNewBit | (uint32_t)p)) mask |= 1u << (c + k);
-          else if (a.agg_src)  // everything but the first occurrences is known now: the local id, or ~p_first
-            a.agg_src[edge_base + p] = (q[k] < kNewBit) ? (int32_t)q[k] : ~(int32_t)(q[k] & ~kNewBit);
+          else if (h.agg_src)  // everything but the first occurrences is known now: the local id, or ~p_first
+            h.agg_src[edge_base + p] = (q[k] < kNewBit) ? (int32_t)q[k] : ~(int32_t)(q[k] & ~kNewBit);
         }
       }
     }
@@ -570,14 +610,14 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
     int32_t total;
     const int32_t mine = block_exclusive_scan(__popc(mask), s_red, &total);
     if (tid == 0) trace_mark(a.trace, tslot, tile, 2);
-    const int32_t excl = block_exclusive_prefix(a.tile_state, a.anchors, tile, total, s_red);
-    if (tid == 0 && tile == n_tiles - 1) a.hs->new_nodes = excl + total;  // C_h (:263)
+    const int32_t excl = block_exclusive_prefix(h.tile_state, h.anchors, tile, total, s_red);
+    if (tid == 0 && tile == n_tiles - 1) h.hs->new_nodes = excl + total;  // C_h (:263)
     if (tid == 0) trace_mark(a.trace, tslot, tile, 3);
     int32_t local = node_base + excl + mine;
     while (mask) {  // first occurrences, in edge order; the vertex is re-read (coalesced, cached) rather than kept
       const int k = __ffs(mask) - 1;
       mask &= mask - 1;
-      const int32_t w = a.gid[p0 + k];
+      const int32_t w = h.gid[p0 + k];
       if (local < a.ids_cap) a.ids[local] = w;  // :270
       else *a.status = 1;
       if (PUBLISH) {  // position_map :271
@@ -589,37 +629,54 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
           st_u32_hint(a.map.pm + w, (uint32_t)local, keep);
         }
       }
-      if (a.agg_src) a.agg_src[edge_base + p0 + k] = local;
+      if (h.agg_src) h.agg_src[edge_base + p0 + k] = local;
       local++;
     }
     if (tid == 0) trace_mark(a.trace, tslot, tile, 4);
   }
+  return true;
+}
 
-  // the op's counter_update (:69-82), by the last CTA to finish
+// the op's counter_update (:69-82), by one thread once every tile of the hop is done
+__device__ __forceinline__ void rank_counter_update(const RankArgs& a, const RankHop& h) {
+  volatile int32_t* nc = a.nc;
+  volatile int32_t* ec = a.ec;
+  const int32_t E = ec[2];
+  const int32_t C = (E > 0) ? *((volatile int32_t*)&h.hs->new_nodes) : 0;
+  const int32_t nc0 = nc[0] + nc[1];
+  nc[0] = nc0;
+  nc[1] = C;
+  nc[LG_INTRABATCH_CON * 2] = 0;
+  nc[LG_INTRABATCH_CON * 2 + 1] = nc0 + C;
+  const int32_t ec0 = ec[0] + ec[1];
+  ec[0] = ec0;
+  ec[1] = E;
+  ec[2] = 0;
+  nc[LG_INTRABATCH_CON * 3 + h.hop] = nc0 + C;
+  ec[LG_INTRABATCH_CON * 3 + h.hop] = ec0 + E;
+}
+
+template <int ITEMS, bool HASHED, bool PUBLISH>
+__global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
+  __shared__ int32_t s_red[kBlock / 32];
+  __shared__ int32_t s_tile, s_last;
+  const int tid = threadIdx.x;
+  pdl_prologue();
+  if (tid == 0) s_tile = atomicAdd(&a.h.hs->rank_ticket, 1);
+  __syncthreads();
+  rank_tile<ITEMS, HASHED, PUBLISH>(a, a.h, s_tile, s_red);
+  // the last CTA to finish updates the counters
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    int32_t done = atomicAdd(&a.hs->rank_done, 1);
+    const int32_t done = atomicAdd(&a.h.hs->rank_done, 1);
     s_last = (done == (int32_t)gridDim.x - 1);
   }
   __syncthreads();
-  if (tid == 0) trace_mark(a.trace, tslot, tile, 7);
+  if (tid == 0) trace_mark(a.trace, (a.h.hop - 1) * 2 + 1, s_tile, 7);
   if (s_last && tid == 0) {
     __threadfence();
-    volatile int32_t* nc = a.nc;
-    volatile int32_t* ec = a.ec;
-    int32_t C = (n_tiles > 0) ? *((volatile int32_t*)&a.hs->new_nodes) : 0;
-    int32_t nc0 = nc[0] + nc[1];
-    nc[0] = nc0;
-    nc[1] = C;
-    nc[LG_INTRABATCH_CON * 2] = 0;
-    nc[LG_INTRABATCH_CON * 2 + 1] = nc0 + C;
-    int32_t ec0 = ec[0] + ec[1];
-    ec[0] = ec0;
-    ec[1] = E;
-    ec[2] = 0;
-    nc[LG_INTRABATCH_CON * 3 + a.hop] = nc0 + C;
-    ec[LG_INTRABATCH_CON * 3 + a.hop] = ec0 + E;
+    rank_counter_update(a, a.h);
   }
 }
 
@@ -657,22 +714,27 @@ __device__ __forceinline__ void release_map(const ReleaseArgs& r) {
 // read (first occurrences, >= 0) are never written here.  For every hop but the last, lg_run_batch (dense layout) folds
 // construct_graph into the next hop's sample kernel instead (which looks the same vertices up anyway).
 // After the last hop nobody reads the position map again: lg_run_batch lets this kernel release it (`rel`).
+__device__ __forceinline__ void relabel_body(int32_t* __restrict__ agg_src, const int32_t* __restrict__ ec, int64_t t,
+                                             int64_t n_threads) {
+  const int32_t off = ec[0], E = ec[1];
+  for (int64_t q0 = t * 4; q0 < E; q0 += n_threads * 4) {
+    const int32_t p0 = (int32_t)q0;
+    int32_t x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) x[k] = (p0 + k < E) ? agg_src[off + p0 + k] : 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)  // L1-cached: first occurrences of hub vertices are read thousands of times
+      y[k] = (x[k] < 0) ? __ldca(agg_src + off + ~x[k]) : x[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (x[k] < 0) agg_src[off + p0 + k] = y[k];
+  }
+}
 __global__ void __launch_bounds__(kBlock) relabel_kernel(int32_t* __restrict__ agg_src, const int32_t* __restrict__ ec,
                                                          const ReleaseArgs rel) {
   pdl_prologue();
   release_map(rel);
-  const int32_t off = ec[0], E = ec[1];
-  const int32_t p0 = (blockIdx.x * kBlock + threadIdx.x) * 4;
-  if (p0 >= E) return;
-  int32_t x[4], y[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) x[k] = (p0 + k < E) ? agg_src[off + p0 + k] : 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++)  // L1-cached: first occurrences of hub vertices are read thousands of times
-    y[k] = (x[k] < 0) ? __ldca(agg_src + off + ~x[k]) : x[k];
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (x[k] < 0) agg_src[off + p0 + k] = y[k];
+  relabel_body(agg_src, ec, (int64_t)blockIdx.x * kBlock + threadIdx.x, (int64_t)gridDim.x * kBlock);
 }
 
 // ClearPosMap (:542-548) as its own launch (lg_io_complete of the op-by-op API): the position-map words of this
@@ -682,6 +744,131 @@ __global__ void __launch_bounds__(kBlock) relabel_kernel(int32_t* __restrict__ a
 __global__ void __launch_bounds__(kBlock) release_kernel(const ReleaseArgs rel) {
   pdl_prologue();
   release_map(rel);
+}
+
+// ------------------------------------------------------------------------------------------
+// chain_kernel (dense layout): the whole sampler chain of one batch — batch_generate, (sample, rank) per hop, the last
+// hop's relabel and the release of the position map — as ONE persistent launch, with grid barriers where the separate
+// kernels had launch boundaries.  Why: every kernel launch on the GPU stalls the gather streaming on the other stream
+// for ~3.8 us, whatever its size (profiles/r01d_overlap.md); 6 launches per batch become 1.
+// 148 x 4 CTAs at <= 40 registers: exactly what fits an SM next to the gather's 12 single-warp CTAs (17 k registers,
+// 130 KB of shared memory), so the grid is co-resident whether or not a gather is running and the barriers cannot wait on
+// a CTA that has no room.  Tiles are claimed through the same tickets as in the separate kernels (a CTA finishes its tile
+// before it claims the next, so the prefix spins still only wait on running CTAs).  Two chain kernels must never be
+// partially resident at the same time (each would spin on CTAs the other leaves no room for): the host orders them with
+// an event per device (chain_order), and the kernel lets its stream successor launch only when it enters its last phase.
+// MEASURED AND NOT ADOPTED (opt-in, LG_CHAIN=1): bit-exact on every parity test, but the chain alone takes 0.141 ms
+// against 0.108 ms for the PDL-chained kernels (40-register cap shared by all phases, a ticket round trip per tile, six
+// grid barriers), and a persistent grid never lets an SM drain, so whichever of chain and gather arrives second waits for
+// the other's shared-memory configuration: pipelined 31.6 M seeds/s (34.1 M with one carve-out for both) against 40.8 M.
+// ------------------------------------------------------------------------------------------
+constexpr int kChainCtasPerSm = 4;
+struct ChainArgs {
+  BatchGenArgs gen;
+  SampleArgs smp;  // the fields common to all hops; the per-hop ones are patched in the kernel
+  RankArgs rnk;
+  ReleaseArgs rel;
+  int32_t n_hops;
+  int32_t fanout[LG_MAX_HOPS];
+  uint32_t magic[LG_MAX_HOPS];
+  int32_t tile_f[LG_MAX_HOPS];
+  int32_t rank_items[LG_MAX_HOPS];
+  u64* sample_state[LG_MAX_HOPS];
+  u64* sample_groups[LG_MAX_HOPS];
+  u64* rank_state[LG_MAX_HOPS];
+  u64* rank_groups[LG_MAX_HOPS];
+  HopState* hs;
+  int32_t* gid[2];
+  unsigned* bar;  // [0] arrivals, [1] generation: persistent across batches, self-resetting
+};
+
+// Grid barrier; `last` runs on one thread of the last CTA to arrive, before anybody is released.
+template <typename F>
+__device__ __forceinline__ void chain_barrier(unsigned* bar, unsigned n_ctas, F last) {
+  __threadfence();  // every thread: its own stores and REDs are performed before the CTA arrives
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned gen = *(volatile unsigned*)(bar + 1);  // read BEFORE arriving
+    __threadfence();
+    if (atomicAdd(bar, 1u) == n_ctas - 1u) {
+      last();
+      atomicExch(bar, 0u);
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*(volatile unsigned*)(bar + 1) == gen) __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  __threadfence();  // every thread: invalidates this SM's L1 (CCTL.IVALL) — the next phase reads other CTAs' results
+}
+
+template <int RNG>
+__global__ void __launch_bounds__(kBlock, 6) chain_kernel(const ChainArgs c) {
+  __shared__ SampleSmem<256> sm;
+  __shared__ int32_t s_tile;
+  const int tid = threadIdx.x;
+  const unsigned n_ctas = gridDim.x;
+  const int64_t gtid = (int64_t)blockIdx.x * kBlock + tid, n_threads = (int64_t)n_ctas * kBlock;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __threadfence();  // see pdl_prologue
+  batch_generate_body<false>(c.gen, (int32_t)gtid, (int32_t)n_threads);
+  chain_barrier(c.bar, n_ctas, [] {});
+  for (int h = 0; h < c.n_hops; h++) {
+    const bool last_hop = (h == c.n_hops - 1);
+    {
+      SampleHop sh;
+      sh.frontier_prev = c.gid[(h + 1) & 1];
+      sh.gid_out = c.gid[h & 1];
+      sh.tile_state = c.sample_state[h];
+      sh.anchors = c.sample_groups[h];
+      sh.hs = c.hs + h;
+      sh.hop = h + 1;
+      sh.fanout = c.fanout[h];
+      sh.fanout_magic = c.magic[h];
+      sh.relabel_prev = h > 0;  // construct_graph of the previous hop rides along (its vertices are looked up anyway)
+      const int tile_f = c.tile_f[h];
+      for (;;) {
+        __syncthreads();  // the previous tile's shared memory and s_tile are free
+        if (tid == 0) s_tile = atomicAdd(&sh.hs->sample_ticket, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        bool more;
+        switch (tile_f) {
+          case 256: more = sample_tile<256, RNG, false>(c.smp, sh, tile, sm); break;
+          case 128: more = sample_tile<128, RNG, false>(c.smp, sh, tile, reinterpret_cast<SampleSmem<128>&>(sm)); break;
+          case 64: more = sample_tile<64, RNG, false>(c.smp, sh, tile, reinterpret_cast<SampleSmem<64>&>(sm)); break;
+          default: more = sample_tile<32, RNG, false>(c.smp, sh, tile, reinterpret_cast<SampleSmem<32>&>(sm)); break;
+        }
+        if (!more) break;
+      }
+    }
+    chain_barrier(c.bar, n_ctas, [] {});
+    RankHop rh;
+    rh.gid = c.gid[h & 1];
+    rh.tile_state = c.rank_state[h];
+    rh.anchors = c.rank_groups[h];
+    rh.hs = c.hs + h;
+    rh.hop = h + 1;
+    rh.agg_src = last_hop ? c.smp.agg_src : nullptr;  // earlier hops: written by the next hop's sample phase
+    const int items = c.rank_items[h];
+    for (;;) {
+      __syncthreads();
+      if (tid == 0) s_tile = atomicAdd(&rh.hs->rank_ticket, 1);
+      __syncthreads();
+      const int tile = s_tile;
+      bool more;
+      if (items == 12)
+        more = last_hop ? rank_tile<12, false, false>(c.rnk, rh, tile, sm.red) : rank_tile<12, false, true>(c.rnk, rh, tile, sm.red);
+      else
+        more = last_hop ? rank_tile<4, false, false>(c.rnk, rh, tile, sm.red) : rank_tile<4, false, true>(c.rnk, rh, tile, sm.red);
+      if (!more) break;
+    }
+    chain_barrier(c.bar, n_ctas, [&] { rank_counter_update(c.rnk, rh); });
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the stream successor may become resident now
+  release_map(c.rel);
+  relabel_body(c.smp.agg_src, c.rnk.ec, gtid, n_threads);
 }
 
 // HotnessMeasure (cache/cache_impl.cuh:190-198) + max_ids_ (cache/cache.cu:59-61)
@@ -711,20 +898,24 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //                    the O(batch) scatter
 //   LG_RED_PRECHECK  1 (default) = dense layout: L1-cached look at the map word before the RED.MIN; skips the RED when the
 //                    word already holds an earlier position (hub vertices: sample hop 2 0.0915 -> 0.0827 ms)
+//   LG_CHAIN         1 = lg_run_batch runs the dense layout's sampler chain as ONE persistent kernel (chain_kernel; read
+//                    when a handle is created).  Opt-in: bit-exact, but measured slower — 34.1 vs 40.8 M seeds/s at best,
+//                    profiles/r01d_chain_kernel.md.  LG_CHAIN_CTAS: its CTAs per SM.
 //   (having a hop's sample kernel also look up the rows of the vertices it samples, so that the next hop starts from two
 //   coalesced arrays, was measured and rejected: hop 1 +5 us, hop 2 -2 us)
 // (A forced shared-memory carve-out on these kernels, LG_CARVEOUT, was measured and rejected: profiles/r01b_overlap.md.)
 struct SamplerTune {
-  int sample_tile, sample_minb, rank_items, pm_fill_mb, red_precheck;
+  int sample_tile, sample_minb, rank_items, pm_fill_mb, red_precheck, chain_ctas;
 };
 static const SamplerTune& sampler_tune() {
   static SamplerTune t = [] {
-    SamplerTune x{0, 6, 0, 16, 1};
+    SamplerTune x{0, 6, 0, 16, 1, kChainCtasPerSm};
     if (const char* e = getenv("LG_SAMPLE_TILE")) x.sample_tile = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_MINB")) x.sample_minb = atoi(e);
     if (const char* e = getenv("LG_RANK_ITEMS")) x.rank_items = atoi(e);
     if (const char* e = getenv("LG_PM_FILL_MB")) x.pm_fill_mb = atoi(e);
     if (const char* e = getenv("LG_RED_PRECHECK")) x.red_precheck = atoi(e);
+    if (const char* e = getenv("LG_CHAIN_CTAS")) x.chain_ctas = atoi(e);
     return x;
   }();
   return t;
@@ -852,6 +1043,9 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   }
   LG_CUDA(cudaMalloc(&s->status, sizeof(int32_t)));
   LG_CUDA(cudaMemset(s->status, 0, sizeof(int32_t)));
+  if (const char* e = getenv("LG_CHAIN")) s->chain = atoi(e) != 0;
+  LG_CUDA(cudaMalloc(&s->chain_bar, 2 * sizeof(unsigned)));
+  LG_CUDA(cudaMemset(s->chain_bar, 0, 2 * sizeof(unsigned)));
   if (s->hashed) LG_CUDA(cudaMalloc(&s->seed_local, (size_t)max_batch * sizeof(int32_t)));
   {
     const char* e = getenv("LG_GATHER_DYNAMIC");
@@ -882,6 +1076,7 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaFree(s->gid[1]);
   cudaFree(s->small);
   cudaFree(s->status);
+  cudaFree(s->chain_bar);
   cudaFreeHost(s->pinned_seeds);
   cudaStreamDestroy(s->side);
   for (int h = 0; h <= LG_MAX_HOPS; h++) cudaEventDestroy(s->ev_fork[h]);
@@ -1020,6 +1215,31 @@ static DedupMap map_of(const lg_sampler* s) {
   return m;
 }
 
+static int32_t clipped_batch_size(int32_t total_cap, int32_t batch_size, int32_t counter) {
+  const long long done = (long long)batch_size * ((long long)counter + 1);
+  int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
+  return size < 0 ? 0 : size;
+}
+static BatchGenArgs batch_gen_args(const lg_sampler* s, const int32_t* all_ids, const int32_t* all_labels, int32_t total_cap,
+                                   int32_t size, int32_t counter, const lg_batch* b) {
+  BatchGenArgs g;
+  g.all_ids = all_ids;
+  g.all_labels = all_labels;
+  g.total_cap = total_cap;
+  g.size = size;
+  g.counter = counter;
+  g.hop_num = s->n_hops;
+  g.ids = b->ids;
+  g.labels = b->labels;
+  g.nc = b->node_counter;
+  g.ec = b->edge_counter;
+  g.map = map_of(s);
+  g.small = (u64*)s->small;
+  g.small_words = (int32_t)(s->small_bytes / 8);
+  g.l2 = lg_l2_hints();
+  return g;
+}
+
 extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32_t* all_ids,
                                  const int32_t* all_labels, int32_t total_cap, int32_t batch_size, int32_t counter,
                                  const lg_batch* b) {
@@ -1037,24 +1257,18 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
   if (s->hashed && !s->table_clean)  // not already re-initialised by the previous batch's last kernel
     LG_CUDA(lg_launch_opt(pdl_on(s, 4), release_kernel, kSMs * 8, kBlock, 0, st, release_args(s, b)));
   s->table_clean = 0;
-  long long done = (long long)batch_size * ((long long)counter + 1);
-  int32_t size = (done >= total_cap) ? (int32_t)(total_cap - (long long)batch_size * counter) : batch_size;  // :159
-  if (size < 0) size = 0;
+  const int32_t size = clipped_batch_size(total_cap, batch_size, counter);
+  const BatchGenArgs g = batch_gen_args(s, all_ids, all_labels, total_cap, size, counter, b);
   int grid = size > 0 ? (size + kBlock - 1) / kBlock : 1;
-  // the kernel also zeroes the per-batch scan state (tickets + tile aggregates): enough threads for one pass
-  const int32_t small_words = (int32_t)(s->small_bytes / 8);
-  const int grid_small = (small_words + kBlock - 1) / kBlock;
+  // the kernel also zeroes the per-batch scan state (tickets + tile words): enough threads for one pass
+  const int grid_small = (g.small_words + kBlock - 1) / kBlock;
   if (grid < grid_small) grid = grid_small < 64 ? grid_small : 64;
   if (s->hashed) {
-    LG_CUDA(lg_launch_opt(pdl_on(s, 4), batch_generate_kernel<true>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
-                      s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
-                      small_words, lg_l2_hints()));
+    LG_CUDA(lg_launch_opt(pdl_on(s, 4), batch_generate_kernel<true>, grid, kBlock, 0, st, g));
     LG_CUDA(lg_launch_opt(pdl_on(s), seed_local_kernel, grid, kBlock, 0, st, (const int32_t*)b->ids, (const int32_t*)b->node_counter,
-                      s->seed_local, map_of(s), lg_l2_hints()));
+                          s->seed_local, map_of(s), lg_l2_hints()));
   } else {
-    LG_CUDA(lg_launch_opt(pdl_on(s, 4), batch_generate_kernel<false>, grid, kBlock, 0, st, all_ids, all_labels, total_cap, size, counter,
-                      s->n_hops, b->ids, b->labels, b->node_counter, b->edge_counter, map_of(s), (u64*)s->small,
-                      small_words, lg_l2_hints()));
+    LG_CUDA(lg_launch_opt(pdl_on(s, 4), batch_generate_kernel<false>, grid, kBlock, 0, st, g));
   }
   s->pm_dirty = 1;
   s->dirty_batch = *b;
@@ -1088,29 +1302,28 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
                       uint64_t rng_seed, uint32_t batch_id, uint32_t stream_id, const lg_batch* b,
                       unsigned long long* edge_hotness, bool relabel_prev, bool relabel_own, bool release) {
   const int h = hop - 1;
-  if (s->hashed) {  // every hop relabels itself; the next hop reads agg_src instead of the table
-    relabel_prev = false;
-    relabel_own = true;
-  }
+  // HASHED: the next hop never reads the table (see seed_local_kernel) but the previous hop's agg_src, which its rank
+  // pass always writes; entries left as ~p_first are patched by relabel_kernel (relabel_own) or by the next hop's
+  // sample kernel (lg_run_batch: one launch less per hop)
   SampleArgs a;
   a.topo = *topo;
-  a.frontier_prev = s->gid[(h + 1) & 1];
+  a.h.frontier_prev = s->gid[(h + 1) & 1];
   a.seed_local = s->seed_local;
-  a.gid_out = s->gid[h & 1];
+  a.h.gid_out = s->gid[h & 1];
   a.ids = b->ids;
   a.agg_src = b->agg_src;
   a.agg_dst = b->agg_dst;
   a.nc = b->node_counter;
   a.ec = b->edge_counter;
   a.map = map_of(s);
-  a.tile_state = s->sample_state[h];
-  a.anchors = s->sample_anchor[h];
-  a.hs = s->hs + h;
+  a.h.tile_state = s->sample_state[h];
+  a.h.anchors = s->sample_anchor[h];
+  a.h.hs = s->hs + h;
   a.edge_hot = (u64*)edge_hotness;
-  a.hop = hop;
-  a.fanout = s->fanout[h];
-  a.fanout_magic = (uint32_t)(((1ull << 32) + (uint64_t)s->fanout[h] - 1) / (uint64_t)s->fanout[h]);
-  a.relabel_prev = relabel_prev ? 1 : 0;
+  a.h.hop = hop;
+  a.h.fanout = s->fanout[h];
+  a.h.fanout_magic = (uint32_t)(((1ull << 32) + (uint64_t)s->fanout[h] - 1) / (uint64_t)s->fanout[h]);
+  a.h.relabel_prev = relabel_prev ? 1 : 0;
   a.precheck = sampler_tune().red_precheck;
   a.batch_id = batch_id;
   a.stream_id = stream_id;
@@ -1126,16 +1339,16 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
     else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
   }
   RankArgs r;
-  r.gid = s->gid[h & 1];
+  r.h.gid = s->gid[h & 1];
   r.ids = b->ids;
   r.nc = b->node_counter;
   r.ec = b->edge_counter;
   r.map = map_of(s);
-  r.agg_src = relabel_own ? b->agg_src : nullptr;
-  r.tile_state = s->rank_state[h];
-  r.anchors = s->rank_anchor[h];
-  r.hs = s->hs + h;
-  r.hop = hop;
+  r.h.agg_src = (relabel_own || s->hashed) ? b->agg_src : nullptr;
+  r.h.tile_state = s->rank_state[h];
+  r.h.anchors = s->rank_anchor[h];
+  r.h.hs = s->hs + h;
+  r.h.hop = hop;
   r.ids_cap = b->num_ids;
   r.l2 = lg_l2_hints();
   r.status = s->status;
@@ -1192,6 +1405,100 @@ extern "C" int lg_io_complete(lg_sampler* s, lg_stream_t stream_, int32_t mode, 
   return clear_position_map(s, st, b);
 }
 
+// ---- chain_kernel launch (lg_run_batch, dense layout) ----
+// Chain kernels of one device are totally ordered by an event (see chain_kernel): a chain on another stream — a second
+// runner in flight — only starts when the previous one has completed.
+namespace {
+struct ChainOrder {
+  std::mutex mu;
+  cudaEvent_t ev[LG_MAX_DEVICE * 2] = {};
+  cudaStream_t last[LG_MAX_DEVICE * 2] = {};
+  bool recorded[LG_MAX_DEVICE * 2] = {};
+} g_chain_order;
+}  // namespace
+
+static bool chain_eligible(const lg_sampler* s, const lg_feature_cache* cache) {
+  if (!s->chain || s->hashed || s->device < 0 || s->device >= LG_MAX_DEVICE * 2) return false;
+  if (cache && s->fuse_gathers != 2) return false;  // gathers between the hops need the hop boundaries
+  for (int h = 0; h < s->n_hops; h++)
+    if (s->rank_items[h] != 4 && s->rank_items[h] != 12) return false;
+  return true;
+}
+
+static int launch_chain(lg_sampler* s, cudaStream_t st, const lg_topology* topo, const lg_batch_params* p, const lg_batch* b) {
+  LG_REQUIRE(p->batch_size <= s->max_batch, "lg_run_batch: batch %d > max_batch %d", p->batch_size, s->max_batch);
+  LG_REQUIRE(b->num_ids >= s->num_ids, "lg_run_batch: batch buffers hold %d ids, need %lld", b->num_ids, (long long)s->num_ids);
+  LG_REQUIRE(p->all_ids && p->all_labels, "lg_run_batch: null seed arrays");
+  if (s->pm_dirty) {  // a previous batch that never reached lg_io_complete still owns position-map words
+    int rc = clear_position_map(s, st, &s->dirty_batch);
+    if (rc) return rc;
+  }
+  if (s->clear_recorded && s->clear_stream != st) LG_CUDA(cudaStreamWaitEvent(st, s->ev_clear, 0));
+  ChainArgs c;
+  memset(&c, 0, sizeof(c));
+  const int32_t size = clipped_batch_size(p->total_cap, p->batch_size, p->counter);
+  c.gen = batch_gen_args(s, p->all_ids, p->all_labels, p->total_cap, size, p->counter, b);
+  SampleArgs& a = c.smp;
+  a.topo = *topo;
+  a.seed_local = nullptr;
+  a.ids = b->ids;
+  a.agg_src = b->agg_src;
+  a.agg_dst = b->agg_dst;
+  a.nc = b->node_counter;
+  a.ec = b->edge_counter;
+  a.map = map_of(s);
+  a.edge_hot = nullptr;
+  a.precheck = sampler_tune().red_precheck;
+  a.batch_id = p->batch_id;
+  a.stream_id = p->stream_id;
+  a.k0 = (uint32_t)p->rng_seed;
+  a.k1 = (uint32_t)(p->rng_seed >> 32);
+  a.l2 = lg_l2_hints();
+  a.trace = s->trace;
+  RankArgs& r = c.rnk;
+  r.ids = b->ids;
+  r.nc = b->node_counter;
+  r.ec = b->edge_counter;
+  r.map = map_of(s);
+  r.ids_cap = b->num_ids;
+  r.l2 = lg_l2_hints();
+  r.status = s->status;
+  r.trace = s->trace;
+  c.rel = release_args(s, b);
+  c.n_hops = s->n_hops;
+  for (int h = 0; h < s->n_hops; h++) {
+    c.fanout[h] = s->fanout[h];
+    c.magic[h] = (uint32_t)(((1ull << 32) + (uint64_t)s->fanout[h] - 1) / (uint64_t)s->fanout[h]);
+    c.tile_f[h] = s->sample_tile_f[h];
+    c.rank_items[h] = s->rank_items[h];
+    c.sample_state[h] = s->sample_state[h];
+    c.sample_groups[h] = s->sample_anchor[h];
+    c.rank_state[h] = s->rank_state[h];
+    c.rank_groups[h] = s->rank_anchor[h];
+  }
+  c.hs = s->hs;
+  c.gid[0] = s->gid[0];
+  c.gid[1] = s->gid[1];
+  c.bar = s->chain_bar;
+  {
+    std::lock_guard<std::mutex> lock(g_chain_order.mu);
+    const int d = s->device;
+    if (!g_chain_order.ev[d]) LG_CUDA(cudaEventCreateWithFlags(&g_chain_order.ev[d], cudaEventDisableTiming));
+    if (g_chain_order.recorded[d] && g_chain_order.last[d] != st) LG_CUDA(cudaStreamWaitEvent(st, g_chain_order.ev[d], 0));
+    int per_sm = sampler_tune().chain_ctas;
+    if (per_sm < 1 || per_sm > 6) per_sm = kChainCtasPerSm;
+    const int grid = kSMs * per_sm;
+    if (p->rng_kind == LG_RNG_MINSTD) LG_CUDA(lg_launch_opt(pdl_on(s), chain_kernel<LG_RNG_MINSTD>, grid, kBlock, 0, st, c));
+    else LG_CUDA(lg_launch_opt(pdl_on(s), chain_kernel<LG_RNG_PHILOX>, grid, kBlock, 0, st, c));
+    LG_CUDA(cudaEventRecord(g_chain_order.ev[d], st));
+    g_chain_order.last[d] = st;
+    g_chain_order.recorded[d] = true;
+  }
+  s->dirty_batch = *b;
+  s->pm_dirty = 1;
+  return released(s, st);  // the kernel's last phase releases the position map
+}
+
 extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology* topo,
                             const lg_feature_cache* cache, const lg_batch_params* p, const lg_batch* b,
                             unsigned long long* tier_rows) {
@@ -1217,11 +1524,13 @@ extern "C" int lg_run_batch(lg_sampler* s, lg_stream_t stream, const lg_topology
     LG_CUDA(cudaEventRecord(s->ev_join, main_st));
     LG_CUDA(cudaStreamWaitEvent(s->side, s->ev_join, 0));
   }
-  int rc = lg_batch_generate(s, stream, p->all_ids, p->all_labels, p->total_cap, p->batch_size, p->counter, b);
+  const bool chain = chain_eligible(s, cache);  // the whole sampler chain as one persistent kernel
+  int rc = chain ? launch_chain(s, main_st, topo, p, b)
+                 : lg_batch_generate(s, stream, p->all_ids, p->all_labels, p->total_cap, p->batch_size, p->counter, b);
   if (rc) return rc;
   int first_pending = 0;  // first hop whose rows have not been gathered yet
   for (int hop = 0; hop <= s->n_hops; hop++) {
-    if (hop > 0) {
+    if (hop > 0 && !chain) {
       // the relabel pass of hop h rides in the sample kernel of hop h+1; only the last hop runs its own
       rc = sample_hop(s, main_st, topo, hop, p->rng_kind, p->rng_seed, p->batch_id, p->stream_id, b, nullptr,
                       /*relabel_prev=*/hop > 1, /*relabel_own=*/hop == s->n_hops, /*release=*/hop == s->n_hops);

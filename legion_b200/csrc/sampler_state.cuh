@@ -30,6 +30,8 @@ struct lg_sampler {
   cudaStream_t clear_stream;   // another stream than the next lg_batch_generate: engine/server.cu puts it on stream 2)
   int32_t clear_recorded;
   int32_t table_clean;         // HASHED: the table was re-initialised by the previous batch's last kernel
+  unsigned* chain_bar;         // DENSE: grid-barrier words of chain_kernel ([0] arrivals, [1] generation)
+  int32_t chain;               // LG_CHAIN=1 at create time: lg_run_batch uses chain_kernel (opt-in: measured slower)
   int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)
   uint8_t* small;        // memset-per-batch region: HopState[hops] + chained-scan tile states
   int64_t small_bytes;

@@ -354,3 +354,36 @@ def test_async_host_fed_batches(oracle):
                 want = orc.run_batch(ids, labels, B, k, seed=6, batch_id=k)
                 assert np.array_equal(cn[k, :16], want["nc"]) and np.array_equal(cn[k, 16:], want["ec"])
                 assert_batch_equal(bufs[k % 2].to_host(2), want, 2, feat)
+
+
+@pytest.mark.parametrize("rng", [capi.RNG_MINSTD, capi.RNG_PHILOX])
+@pytest.mark.parametrize("fanout,batch", [([25, 10], 256), ([15, 10, 5], 100), ([3], 17)])
+def test_chain_kernel_matches_oracle(oracle, monkeypatch, dedup_layout, rng, fanout, batch):
+    """LG_CHAIN=1 (opt-in): the dense layout's whole sampler chain as one persistent kernel with grid barriers
+    (csrc/sampler.cu chain_kernel); same batches, bit for bit, also with two runners in flight on one GPU"""
+    if dedup_layout != "dense":
+        pytest.skip("chain_kernel exists for the dense position map only")
+    monkeypatch.setenv("LG_CHAIN", "1")
+    indptr, indices = small_graph(3000, 14.0, 400)
+    N = len(indptr) - 1
+    feat = _feat(N)
+    ids, labels = make_sets(N)
+    rigs = [Rig(indptr, indices, feat, fanout, batch) for _ in range(2)]
+    for r in rigs:
+        r.dp.set_gather_fusion(2)  # one gather per batch: the chain has no hop boundaries to gather at
+    streams = [torch.cuda.Stream() for _ in rigs]
+    bufs = [r.dp.alloc_batch() for r in rigs]
+    sets = [r.sets(ids, labels) for r in rigs]
+    orc = oracle.Oracle(indptr, indices, fanout, batch)
+    for rnd in range(3):
+        for k, rig in enumerate(rigs):  # both runners enqueue before anybody synchronises
+            counter = 2 * rnd + k
+            with torch.cuda.stream(streams[k]):
+                p = rig.dp.params(sets[k][0], sets[k][1], batch, counter, rng_kind=rng, seed=77, batch_id=counter, stream_id=1)
+                rig.dp.run_once(p, bufs[k])
+        torch.cuda.synchronize()
+        for k, rig in enumerate(rigs):
+            counter = 2 * rnd + k
+            want = orc.run_batch(ids, labels, batch, counter, rng_kind=rng, seed=77, batch_id=counter, stream_id=1)
+            assert_batch_equal(bufs[k].to_host(len(fanout)), want, len(fanout), feat)
+    assert all(r.dp.status() == 0 for r in rigs)
