@@ -134,6 +134,12 @@ int lg_sampler_set_gather_fusion(lg_sampler* s, int32_t mode);
  * reference's two INTERBATCH_CON slots: the last gather of batch k overlaps the sampling of batch
  * k+1; a consumer (or anyone reusing the buffers on another stream) calls lg_batch_wait first. */
 int lg_sampler_set_overlap(lg_sampler* s, int32_t mode);
+/* Lazy construct_graph for the op-by-op calls (default 0 = every lg_random_sample leaves its hop complete, like the
+ * reference's RandomSample op, engine/operator_impl.cu:400-499).  1 = a host that only hands the batch on after the
+ * last op (the server: IPCPost follows the last op) lets hop h's agg_src be finished by hop h+1's sample kernel, and
+ * the last hop's relabel kernel also releases the position map (lg_io_complete then has nothing left to launch):
+ * two kernel launches less per batch, same final buffers and counters. */
+int lg_sampler_set_lazy_relabel(lg_sampler* s, int32_t mode);
 /* make `stream` wait until the batch last produced into `batch` is complete (mode 2; no-op otherwise) */
 int lg_batch_wait(lg_sampler* s, lg_stream_t stream, const lg_batch* batch);
 /* sticky overflow status (0 ok, 1 ids overflow, 3 cache miss without a backing matrix, 2 features buffer too small — the reference

@@ -53,6 +53,7 @@ _PROTOS = {
     "lg_sampler_dedup_layout": (C.c_int32, [vp]),
     "lg_sampler_set_gather_variant": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_overlap": (C.c_int, [vp, C.c_int32]),
+    "lg_sampler_set_lazy_relabel": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_gather_fusion": (C.c_int, [vp, C.c_int32]),
     "lg_debug_spin": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int64]),
     "lg_debug_set_trace": (C.c_int, [vp, vp]),

@@ -1119,6 +1119,13 @@ extern "C" int lg_sampler_set_gather_fusion(lg_sampler* s, int32_t mode) {
   return 0;
 }
 
+extern "C" int lg_sampler_set_lazy_relabel(lg_sampler* s, int32_t mode) {
+  LG_REQUIRE(s, "null sampler");
+  LG_REQUIRE(mode == 0 || mode == 1, "lazy relabel mode %d", mode);
+  s->lazy_relabel = mode;
+  return 0;
+}
+
 extern "C" int lg_sampler_set_overlap(lg_sampler* s, int32_t mode) {
   LG_REQUIRE(s, "null sampler");
   LG_REQUIRE(mode >= 0 && mode <= 2, "overlap mode %d", mode);
@@ -1386,8 +1393,9 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
   LG_REQUIRE(!topo->directory || topo->shard_rows > 0, "lg_random_sample: directory without shard_rows");
   LG_REQUIRE(topo->num_nodes <= s->num_nodes, "lg_random_sample: topology has %lld vertices, sampler was created for %lld",
              (long long)topo->num_nodes, (long long)s->num_nodes);
+  const bool lazy = s->lazy_relabel != 0, last = hop == s->n_hops;
   return sample_hop(s, (cudaStream_t)stream_, topo, hop, rng_kind, rng_seed, batch_id, stream_id, b, edge_hotness,
-                    /*relabel_prev=*/false, /*relabel_own=*/true, /*release=*/false);
+                    /*relabel_prev=*/lazy && hop > 1, /*relabel_own=*/!lazy || last, /*release=*/lazy && last);
 }
 
 extern "C" int lg_io_submit(lg_sampler*, lg_stream_t, int32_t, const lg_batch*) { return 0; }

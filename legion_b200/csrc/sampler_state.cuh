@@ -54,6 +54,7 @@ struct lg_sampler {
   cudaEvent_t ev_join;
   int32_t fuse_gathers;  // lg_run_batch: 0 = one gather per op (reference schedule); 1 = seeds' rows ride with hop 1;
                          // 2 = a single gather of all rows after the last hop
+  int32_t lazy_relabel;  // op-by-op calls: hop h's construct_graph is finished by hop h+1 (lg_sampler_set_lazy_relabel)
   int32_t overlap;  // 0 one stream, 1 fork/join inside a batch, 2 pipelined across batches (see lg_batch_wait)
   // pipelined mode: completion event of the last batch that used a given set of buffers
   struct Done {

@@ -139,6 +139,11 @@ class GPURunner : public Runner {
     if (const char* e = std::getenv("LEGION_RNG")) memorypool_->rng_kind = std::strcmp(e, "minstd") == 0 ? LG_RNG_MINSTD : LG_RNG_PHILOX;
     if (const char* e = std::getenv("LEGION_SEED")) memorypool_->rng_seed = std::strtoull(e, nullptr, 0);
     if (const char* e = std::getenv("LEGION_GATHER")) LGCHECK(lg_sampler_set_gather_variant(memorypool_->sampler, std::atoi(e)));
+    {  // the trainer only sees a batch after its last op: let hop h+1 finish hop h's construct_graph and the last
+       // sampling op release the position map (two launches less per batch); LEGION_LAZY_RELABEL=0 = every op complete
+      const char* e = std::getenv("LEGION_LAZY_RELABEL");
+      LGCHECK(lg_sampler_set_lazy_relabel(memorypool_->sampler, (e && std::atoi(e) == 0) ? 0 : 1));
+    }
     float_feature_len_ = feature->GetFloatFeatureLen();
     max_batch_ = max_batch;
     env->InitializeSamplesBuffer(max_batch, num_ids_, float_feature_len_, local_dev_id_, interbatch_concurrency_);

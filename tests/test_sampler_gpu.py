@@ -387,3 +387,38 @@ def test_chain_kernel_matches_oracle(oracle, monkeypatch, dedup_layout, rng, fan
             want = orc.run_batch(ids, labels, batch, counter, rng_kind=rng, seed=77, batch_id=counter, stream_id=1)
             assert_batch_equal(bufs[k].to_host(len(fanout)), want, len(fanout), feat)
     assert all(r.dp.status() == 0 for r in rigs)
+
+
+@pytest.mark.parametrize("fanout,batch", [([6, 4], 50), ([15, 10, 5], 100), ([7], 33)])
+def test_lazy_relabel_op_by_op(oracle, fanout, batch):
+    """lg_sampler_set_lazy_relabel(1) (what the server runs): hop h's construct_graph is finished by hop h+1's sample
+    kernel, the last sampling op also releases the position map, the lookup of all hops is one launch at the end
+    (LEGION_FUSE_GATHERS).  Counters after every sampling op and the final batch equal the oracle's; several batches on one
+    handle prove the release."""
+    indptr, indices = small_graph()
+    N = len(indptr) - 1
+    feat = _feat(N)
+    ids, labels = make_sets(N)
+    rig = Rig(indptr, indices, feat, fanout, batch)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    L, dp = rig.dp.L, rig.dp
+    st = dp._stream()
+    H = len(fanout)
+    capi.check(L.lg_sampler_set_lazy_relabel(dp.sampler, 1))
+    orc = oracle.Oracle(indptr, indices, fanout, batch)
+    for counter in (0, 1, 4):
+        want = orc.run_batch(ids, labels, batch, counter, seed=9, batch_id=counter, per_hop=True)
+        trace = {op: (nc, ec) for op, nc, ec in want["trace"]}
+        capi.check(L.lg_batch_generate(dp.sampler, st, d_ids.data_ptr(), d_lab.data_ptr(), len(ids), batch, counter, C.byref(buf.c)))
+        for hop in range(1, H + 1):
+            capi.check(L.lg_random_sample(dp.sampler, st, C.byref(dp.topo), hop, capi.RNG_PHILOX, 9, counter, 0, C.byref(buf.c), None))
+            torch.cuda.synchronize()
+            nc, ec = buf.node_counter.cpu().numpy(), buf.edge_counter.cpu().numpy()
+            # the lookup ops in between are skipped, so only the cumulative per-hop totals are compared here
+            assert np.array_equal(nc[9:], trace[3 * hop][0][9:]) and np.array_equal(ec[9:], trace[3 * hop][1][9:]), hop
+        capi.check(L.lg_feature_cache_lookup_range(dp.sampler, st, C.byref(dp.cache), 3 * H + 1, 0, 0, C.byref(buf.c), None))
+        capi.check(L.lg_io_complete(dp.sampler, st, capi.TRAINMODE, C.byref(buf.c), None, None))
+        torch.cuda.synchronize()
+        assert_batch_equal(buf.to_host(H), want, H, feat)
+    assert dp.status() == 0
