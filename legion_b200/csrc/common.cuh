@@ -182,35 +182,4 @@ __device__ __forceinline__ int32_t warp_incl_scan(int32_t v, int lane) {
   return v;
 }
 
-// ---- single-pass chained scan (decoupled look-back).  state[t] = flag<<32 | value,
-//      flag 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.  Called by one full warp;
-//      tiles are claimed through an atomic ticket so every predecessor is already running. ----
-__device__ __forceinline__ int32_t lookback_exclusive(u64* state, int tile, int32_t aggregate, int lane) {
-  if (tile == 0) {
-    if (lane == 0) st_relaxed(state, (2ull << 32) | (uint32_t)aggregate);
-    return 0;
-  }
-  if (lane == 0) st_relaxed(state + tile, (1ull << 32) | (uint32_t)aggregate);
-  int32_t excl = 0;
-  int look = tile - 1;
-  while (true) {
-    int idx = look - lane;
-    u64 s = (idx >= 0) ? ld_relaxed(state + idx) : (2ull << 32);
-    while (__any_sync(0xffffffffu, (s >> 32) == 0ull)) {
-      if ((s >> 32) == 0ull) s = ld_relaxed(state + idx);
-    }
-    unsigned done = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
-    int32_t v = (int32_t)(uint32_t)s;
-    if (done) {
-      int first = __ffs(done) - 1;
-      excl += warp_sum(lane <= first ? v : 0);
-      break;
-    }
-    excl += warp_sum(v);
-    look -= 32;
-  }
-  if (lane == 0) st_relaxed(state + tile, (2ull << 32) | (uint32_t)(excl + aggregate));
-  return excl;
-}
-
 }  // namespace lg

@@ -30,7 +30,8 @@
 //           every one of the ~10 M map accesses of a batch is a random DRAM access; the table keeps them in L2.
 //           Insert-min is ONE returning atomicMin per probe on the packed word: an empty slot (all ones) or the
 //           same key take the minimum directly; a larger resident key is displaced and carried to the next slot
-//           (linear probing, no CAS, no pre-read).  The table is re-initialised by one 32 MB memset per batch.
+//           (linear probing, no CAS, no pre-read).  The table is re-initialised by one 32 MB streaming fill per batch
+//           (release_map, run by the batch's last kernel).
 #include "common.cuh"
 #include "sampler_state.cuh"
 

@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-struct HopState {  // zeroed once per batch (one cudaMemsetAsync over the whole small region)
+struct HopState {  // zeroed once per batch (batch_generate_body zeroes the whole small region)
   int32_t sample_ticket;
   int32_t rank_ticket;
   int32_t rank_done;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # end-of-round visit: what the driver runs (GPU tests, smoke, both bench arms) + the ncu evidence for profiles/
 set -u
-TAG=${TAG:-r01d}
+TAG=${TAG:-r01e}
 mkdir -p gpurun_out
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
