@@ -145,6 +145,9 @@ int lg_batch_wait(lg_sampler* s, lg_stream_t stream, const lg_batch* batch);
 /* sticky overflow status (0 ok, 1 ids overflow, 3 cache miss without a backing matrix, 2 features buffer too small — the reference
  * sizes it 1.2 x presampled max without a bound check, engine/server.cu:277).  Synchronises. */
 int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);
+/* the same copy without the synchronisation: `pinned_host_status` (page-locked) holds the flag once the work enqueued on
+ * `stream` so far has completed — a pipelined host reads it after the event it waits for anyway */
+int lg_sampler_status_async(lg_sampler* s, lg_stream_t stream, int32_t* pinned_host_status);
 
 /* diagnostics: per-tile phase timestamps of the sampler kernels (globaltimer ns, clock64) written to a device
  * buffer of lg_debug_trace_words() u64 words, layout [(hop-1)*2 + kernel][tile < 2048][phase < 8][2]; NULL = off */

@@ -60,6 +60,7 @@ _PROTOS = {
     "lg_debug_trace_words": (C.c_int64, []),
     "lg_batch_wait": (C.c_int, [vp, vp, C.POINTER(Batch)]),
     "lg_sampler_status": (C.c_int, [vp, vp, C.POINTER(C.c_int32)]),
+    "lg_sampler_status_async": (C.c_int, [vp, vp, vp]),
     "lg_batch_generate": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Batch)]),
     "lg_random_sample": (C.c_int, [vp, vp, C.POINTER(Topology), C.c_int32, C.c_int32, C.c_uint64, C.c_uint32,
                                    C.c_uint32, C.POINTER(Batch), vp]),

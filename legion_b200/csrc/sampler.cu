@@ -1166,6 +1166,12 @@ extern "C" int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* hos
   return 0;
 }
 
+extern "C" int lg_sampler_status_async(lg_sampler* s, lg_stream_t stream, int32_t* pinned_host_status) {
+  LG_REQUIRE(s && pinned_host_status, "null argument");
+  LG_CUDA(cudaMemcpyAsync(pinned_host_status, s->status, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int32_t lg_sampler_dedup_layout(const lg_sampler* s) { return s ? s->hashed : -1; }
 
 extern "C" int64_t lg_sampler_scratch_bytes(const lg_sampler* s) {

@@ -160,6 +160,15 @@ class GPURunner : public Runner {
       b->num_ids = num_ids_;
       b->feature_rows = 0;
     }
+    status_host_.assign(interbatch_concurrency_, nullptr);
+    status_ev_.resize(interbatch_concurrency_);
+    for (int i = 0; i < interbatch_concurrency_; i++) {
+      void* h = nullptr;
+      LGCHECK(lg_host_alloc_mapped(&h, nullptr, sizeof(int32_t)));
+      status_host_[i] = (int32_t*)h;
+      *status_host_[i] = 0;
+      LGCHECK(lg_event_create(&status_ev_[i]));
+    }
     events_.resize(interbatch_concurrency_);
     for (auto& ev : events_) {
       ev.resize(op_num_);
@@ -236,6 +245,10 @@ class GPURunner : public Runner {
       op_params_[i]->event = ev[i];
       ops_[i]->run(op_params_[i]);
     }
+    // the sticky overflow flag as of this batch's last lookup: an asynchronous copy behind it (a synchronous read on any
+    // of the three streams would wait for the batch just launched, not for the one being handed off)
+    LGCHECK(lg_sampler_status_async(memorypool_->sampler, streams_[1], status_host_[current_pipe_]));
+    LGCHECK(lg_event_record(status_ev_[current_pipe_], streams_[1]));
     if (pending_pipe_ >= 0) Complete(env, pending_pipe_, pending_batch_);
     pending_pipe_ = current_pipe_;
     pending_batch_ = batch_id;
@@ -250,8 +263,8 @@ class GPURunner : public Runner {
     auto& ev = events_[pipe];
     for (int i = op_num_ - INTRABATCH_CON; i < op_num_; i++)  // join all three streams before the hand-off
       LGCHECK(lg_event_synchronize(ev[i]));
-    int32_t st = 0;
-    LGCHECK(lg_sampler_status(memorypool_->sampler, streams_[2], &st));  // sticky flag; stream 2 is idle
+    LGCHECK(lg_event_synchronize(status_ev_[pipe]));
+    const int32_t st = *status_host_[pipe];
     if (st != 0) {
       std::fprintf(stderr, "batch %d on GPU %d overflowed its buffers (status %d)\n", batch_id, local_dev_id_, st);
       std::exit(EXIT_FAILURE);
@@ -270,6 +283,8 @@ class GPURunner : public Runner {
     lg_sampler_destroy(memorypool_->sampler);
     for (auto& ev : events_)
       for (auto& e : ev) lg_event_destroy(e);
+    for (auto& e : status_ev_) lg_event_destroy(e);
+    for (auto* h : status_host_) lg_host_free(h);
     for (auto& s : streams_) lg_stream_destroy(s);
   }
 
@@ -281,6 +296,8 @@ class GPURunner : public Runner {
   std::vector<std::vector<lg_event_t>> events_;  // [slot][op]
   int pending_pipe_ = -1;
   int32_t pending_batch_ = 0;
+  std::vector<int32_t*> status_host_;  // [slot] pinned copy of the sampler's sticky status
+  std::vector<lg_event_t> status_ev_;
   std::vector<Operator*> ops_;
   std::vector<OpParams*> op_params_;
 };
