@@ -45,7 +45,6 @@ constexpr uint32_t kPmEmpty = 0xFFFFFFFFu;  // position-map word of a vertex not
 constexpr uint32_t kNewBit = 0x80000000u;   // kNewBit | first edge position while a hop is open; final local ids are < 2^31
 constexpr int kBlock = 256;
 constexpr int kSlotUnroll = 5;              // neighbour reads in flight per thread in sample_hop_kernel
-constexpr bool kHashPrecheck = false;      // L1-cached pre-read before the atomic: +3% on a hub-heavy 2.4 M-vertex graph, -5% at UK-Union scale (the regime HASHED is for)
 constexpr int kSlotUnrollHashed = 5;        // HASHED: 10 in flight was measured slower (registers): 0.195 vs 0.174 ms for hop 2 at UK-Union scale
 
 // optional per-tile phase timestamps (diagnostics only: lg_debug_set_trace; nullptr in production)
@@ -434,7 +433,7 @@ __device__ __forceinline__ bool sample_tile(const SampleArgs& a, const SampleHop
           a.agg_dst[edge_base + p[u]] = fl[u];  // construct_graph :292,294
           sl[u] = map_home(a.map, (uint32_t)w[u]);
           carry[u] = map_pack((uint32_t)w[u], kNewBit | (uint32_t)p[u]);
-          if (kHashPrecheck) {  // L1-cached look first: a word that already holds this vertex with an earlier position needs no atomic
+          if (a.precheck & 2) {  // L1-cached look first: a word that already holds this vertex with an earlier position needs no atomic
             const u64 cur = ld_ca_u64_hint(a.map.table + sl[u], keep);
             old[u] = ((uint32_t)(cur >> 32) == (uint32_t)w[u] && cur <= carry[u]) ? cur
                                                                                    : atom_min_u64_hint(a.map.table + sl[u], carry[u], keep);
@@ -475,7 +474,7 @@ __device__ __forceinline__ bool sample_tile(const SampleArgs& a, const SampleHop
           }
         }
       }
-    } else if (a.precheck) {
+    } else if (a.precheck & 1) {
       // a word that already holds an earlier position (or a final id) needs no RED: hub vertices are sampled thousands
       // of times per hop, and their REDs serialise on one L2 slice.  A stale L1 line only holds a LARGER value than
       // the word has now (values only decrease while a hop is open), so skipping on `cur <= val` is always right.
@@ -897,8 +896,10 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8, 12 or 16; default 12 dense, 16 hashed: one wave)
 //   LG_PM_FILL_MB    dense position maps up to this size (default 16 MB) are released by a streaming fill instead of
 //                    the O(batch) scatter
-//   LG_RED_PRECHECK  1 (default) = dense layout: L1-cached look at the map word before the RED.MIN; skips the RED when the
-//                    word already holds an earlier position (hub vertices: sample hop 2 0.0915 -> 0.0827 ms)
+//   LG_RED_PRECHECK  bit 0 (default on) = dense layout: L1-cached look at the map word before the RED.MIN; skips the RED when
+//                    the word already holds an earlier position (hub vertices: sample hop 2 0.0915 -> 0.0827 ms);
+//                    bit 1 = the same before the hashed layout's atomicMin (off: an earlier version measured +3 % on a
+//                    hub-heavy 2.4 M-vertex graph, -5 % at UK-Union scale — the regime the hashed layout is for)
 //   LG_CHAIN         1 = lg_run_batch runs the dense layout's sampler chain as ONE persistent kernel (chain_kernel; read
 //                    when a handle is created).  Opt-in: bit-exact, but measured slower — 34.1 vs 40.8 M seeds/s at best,
 //                    profiles/r01d_chain_kernel.md.  LG_CHAIN_CTAS: its CTAs per SM.

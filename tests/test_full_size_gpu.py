@@ -113,3 +113,30 @@ def test_full_size_three_hops_minstd(oracle, products):
     assert np.array_equal(buf.agg_src[:e].cpu().numpy(), want["agg_src"][:e])
     assert np.array_equal(buf.agg_dst[:e].cpu().numpy(), want["agg_dst"][:e])
     dp.close()
+
+
+@pytest.mark.parametrize("B,fanout", [(1000, [20, 10]), (2500, [20, 4]), (600, [30, 30])])
+def test_mid_size_frontiers(oracle, products, B, fanout):
+    """frontier lengths that select the 64- and 128-entry sample tiles and the 8/12/16-edge rank tiles
+    (csrc/sampler.cu pick_tile_f / pick_rank_items): 20 k, 50 k and 18 k entries; two batches each, bit-exact"""
+    g = products
+    dp = DataPath(0, fanout, B, g["N"], g["D"])
+    dp.set_full_graph(g["ip"].data_ptr(), g["ix"].data_ptr())
+    dp.set_backing_features(g["feat"].data_ptr())
+    buf = dp.alloc_batch(feature_rows=1)
+    orc = oracle.Oracle(g["ip"].cpu().numpy(), g["ix"].cpu().numpy(), fanout, B)
+    labels = (g["train"] % 47).astype(np.int32)
+    for counter in (2, 5):
+        p = dp.params(g["d_train"], g["d_lab"], B, counter, seed=SEED, batch_id=counter)
+        dp.run_once(p, buf, gather=False)
+        torch.cuda.synchronize()
+        assert dp.status() == 0
+        want = orc.run_batch(g["train"], labels, B, counter, seed=SEED, batch_id=counter)
+        nc, ec = buf.node_counter.cpu().numpy(), buf.edge_counter.cpu().numpy()
+        H = len(fanout)
+        assert np.array_equal(nc[9:], want["nc"][9:]) and np.array_equal(ec, want["ec"])
+        n, e = int(nc[9 + H]), int(ec[9 + H])
+        assert np.array_equal(buf.ids[:n].cpu().numpy(), want["ids"][:n])
+        assert np.array_equal(buf.agg_src[:e].cpu().numpy(), want["agg_src"][:e])
+        assert np.array_equal(buf.agg_dst[:e].cpu().numpy(), want["agg_dst"][:e])
+    dp.close()
