@@ -960,6 +960,10 @@ static int pick_rank_items(int64_t edges_max, bool hashed) {
   return hashed ? 16 : 12;
 }
 
+static int sampler_init(lg_sampler* s, int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
+                        int64_t num_nodes);
+extern "C" int lg_sampler_destroy(lg_sampler* s);
+
 extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
                                  int64_t num_nodes, lg_sampler** out) {
   LG_REQUIRE(out && fanout, "lg_sampler_create: null argument");
@@ -970,6 +974,17 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_CUDA(cudaSetDevice(device));
   lg_sampler* s = new lg_sampler();
   memset(s, 0, sizeof(*s));
+  const int rc = sampler_init(s, device, max_batch, fanout, n_hops, num_nodes);
+  if (rc) {  // nothing of a half-built handle survives (every member is null or owned)
+    lg_sampler_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return 0;
+}
+
+static int sampler_init(lg_sampler* s, int32_t device, int32_t max_batch, const int32_t* fanout, int32_t n_hops,
+                        int64_t num_nodes) {
   s->device = device;
   s->max_batch = max_batch;
   s->n_hops = n_hops;
@@ -1063,7 +1078,6 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_CUDA(cudaEventCreateWithFlags(&s->ev_clear, cudaEventDisableTiming));
   s->overlap = 1;
   s->fuse_gathers = 1;
-  *out = s;
   return 0;
 }
 
@@ -1080,10 +1094,11 @@ extern "C" int lg_sampler_destroy(lg_sampler* s) {
   cudaFree(s->status);
   cudaFree(s->chain_bar);
   cudaFreeHost(s->pinned_seeds);
-  cudaStreamDestroy(s->side);
-  for (int h = 0; h <= LG_MAX_HOPS; h++) cudaEventDestroy(s->ev_fork[h]);
-  cudaEventDestroy(s->ev_join);
-  cudaEventDestroy(s->ev_clear);
+  if (s->side) cudaStreamDestroy(s->side);  // a half-built handle (lg_sampler_create failed) has null members
+  for (int h = 0; h <= LG_MAX_HOPS; h++)
+    if (s->ev_fork[h]) cudaEventDestroy(s->ev_fork[h]);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
+  if (s->ev_clear) cudaEventDestroy(s->ev_clear);
   for (int i = 0; i < s->n_done; i++) cudaEventDestroy(s->done[i].ev);
   delete s;
   return 0;
