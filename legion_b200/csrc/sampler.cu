@@ -1072,6 +1072,8 @@ static int sampler_init(lg_sampler* s, int32_t device, int32_t max_batch, const 
     }
   }
   LG_CUDA(cudaMallocHost(&s->pinned_seeds, (size_t)max_batch * 2 * sizeof(int32_t)));
+  // (stream priorities were measured: the side stream at the highest priority 41.6 -> 40.0 M seeds/s, the callers'
+  // sampling streams at the highest priority 41.5-42.9 -> 40.2 M: any asymmetry loses, profiles/r01d_overlap.md)
   LG_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   for (int h = 0; h <= LG_MAX_HOPS; h++) LG_CUDA(cudaEventCreateWithFlags(&s->ev_fork[h], cudaEventDisableTiming));
   LG_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
