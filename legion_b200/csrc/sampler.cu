@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //                    6 CTAs fit an SM: the 782 tiles of a 200 k-entry frontier run as one wave (592 slots otherwise)
 //   LG_RANK_ITEMS    edges per thread of the long hops' rank kernel (4, 8, 12 or 16; default 12 dense, 16 hashed: one wave)
 //   LG_PM_FILL_MB    dense position maps up to this size (default 16 MB) are released by a streaming fill instead of
-//                    the O(batch) scatter
+//                    the O(batch) scatter (read when a handle is created)
 //   LG_RED_PRECHECK  bit 0 (default on) = dense layout: L1-cached look at the map word before the RED.MIN; skips the RED when
 //                    the word already holds an earlier position (hub vertices: sample hop 2 0.0915 -> 0.0827 ms);
 //                    bit 1 = the same before the hashed layout's atomicMin (off: an earlier version measured +3 % on a
@@ -907,15 +907,14 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //   coalesced arrays, was measured and rejected: hop 1 +5 us, hop 2 -2 us)
 // (A forced shared-memory carve-out on these kernels, LG_CARVEOUT, was measured and rejected: profiles/r01b_overlap.md.)
 struct SamplerTune {
-  int sample_tile, sample_minb, rank_items, pm_fill_mb, red_precheck, chain_ctas;
+  int sample_tile, sample_minb, rank_items, red_precheck, chain_ctas;
 };
 static const SamplerTune& sampler_tune() {
   static SamplerTune t = [] {
-    SamplerTune x{0, 6, 0, 16, 1, kChainCtasPerSm};
+    SamplerTune x{0, 6, 0, 1, kChainCtasPerSm};
     if (const char* e = getenv("LG_SAMPLE_TILE")) x.sample_tile = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_MINB")) x.sample_minb = atoi(e);
     if (const char* e = getenv("LG_RANK_ITEMS")) x.rank_items = atoi(e);
-    if (const char* e = getenv("LG_PM_FILL_MB")) x.pm_fill_mb = atoi(e);
     if (const char* e = getenv("LG_RED_PRECHECK")) x.red_precheck = atoi(e);
     if (const char* e = getenv("LG_CHAIN_CTAS")) x.chain_ctas = atoi(e);
     return x;
@@ -1061,6 +1060,8 @@ static int sampler_init(lg_sampler* s, int32_t device, int32_t max_batch, const 
   LG_CUDA(cudaMalloc(&s->status, sizeof(int32_t)));
   LG_CUDA(cudaMemset(s->status, 0, sizeof(int32_t)));
   if (const char* e = getenv("LG_CHAIN")) s->chain = atoi(e) != 0;
+  s->pm_fill_mb = 16;
+  if (const char* e = getenv("LG_PM_FILL_MB")) s->pm_fill_mb = atoi(e);
   LG_CUDA(cudaMalloc(&s->chain_bar, 2 * sizeof(unsigned)));
   LG_CUDA(cudaMemset(s->chain_bar, 0, 2 * sizeof(unsigned)));
   if (s->hashed) LG_CUDA(cudaMalloc(&s->seed_local, (size_t)max_batch * sizeof(int32_t)));
@@ -1206,7 +1207,7 @@ static ReleaseArgs release_args(const lg_sampler* s, const lg_batch* b) {
   if (s->hashed) {  // O(batch)-sized table, L2-resident: one streaming fill instead of an O(batch) random clear
     r.fill = (uint4*)s->table;
     r.n16 = ((int64_t)s->table_mask + 1) / 2;
-  } else if (s->num_nodes * 4 <= (int64_t)sampler_tune().pm_fill_mb * (1ll << 20)) {
+  } else if (s->num_nodes * 4 <= (int64_t)s->pm_fill_mb * (1ll << 20)) {
     r.fill = (uint4*)s->pm;
     r.n16 = (s->num_nodes + 3) / 4;
   } else {

@@ -31,6 +31,7 @@ struct lg_sampler {
   int32_t clear_recorded;
   int32_t table_clean;         // HASHED: the table was re-initialised by the previous batch's last kernel
   unsigned* chain_bar;         // DENSE: grid-barrier words of chain_kernel ([0] arrivals, [1] generation)
+  int32_t pm_fill_mb;          // DENSE maps up to this size are released by a streaming fill (LG_PM_FILL_MB at create time)
   int32_t chain;               // LG_CHAIN=1 at create time: lg_run_batch uses chain_kernel (opt-in: measured slower)
   int32_t* gid[2];       // double-buffered hop-relative global ids (next frontier)
   uint8_t* small;        // memset-per-batch region: HopState[hops] + chained-scan tile states

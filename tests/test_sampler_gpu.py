@@ -122,9 +122,12 @@ def test_tail_padding_minus_one(oracle):
     assert_batch_equal(buf.to_host(2), want, 2)
 
 
-def test_position_map_is_released_between_batches(oracle):
-    """the O(N) position map is never memset: every batch must leave it all-absent (ClearPosMap,
-    engine/operator_impl.cu:542-548), also when a batch is abandoned after batch_generate or mid-way"""
+@pytest.mark.parametrize("release", ["fill", "scatter"])
+def test_position_map_is_released_between_batches(oracle, monkeypatch, release):
+    """every batch must leave the position map all-absent (ClearPosMap, engine/operator_impl.cu:542-548), also when a
+    batch is abandoned after batch_generate or mid-way; both release paths of the dense layout: the streaming fill
+    (maps of a few MB) and the O(batch) scatter over the batch's vertices (LG_PM_FILL_MB=0: what larger maps use)"""
+    monkeypatch.setenv("LG_PM_FILL_MB", "16" if release == "fill" else "0")
     indptr, indices = small_graph(3000, 14.0, 400)
     N = len(indptr) - 1
     ids, labels = make_sets(N)
