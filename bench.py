@@ -250,13 +250,16 @@ def run_ours(args):
             kg *= 2
     assert world % kg == 0, "world size must be a multiple of Kg"
     # rows cached across the clique: the whole table, or its hottest --cache-ratio fraction (misses -> pinned host)
-    cap = (int(N * min(args.cache_ratio, 1.0)) + kg - 1) // kg
-    cap = max(cap, 1)
+    # --replicate-ratio r: the hottest r*N rows are stored on EVERY GPU of the clique (local reads for the head of the
+    # distribution), only the rest of the cached rows is partitioned (hybrid placement, lg_place_features_hybrid)
+    cached_rows = int(N * min(args.cache_ratio, 1.0))
+    rep = min(int(N * max(args.replicate_ratio, 0.0)), cached_rows) if kg > 1 else 0
+    cap = max(rep + (cached_rows - rep + kg - 1) // kg, 1)
     if feat is not None and not feat_host:
-        dp.build_feature_cache(order, cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None)
+        dp.build_feature_cache(order, cap, kg=kg, j=rank % kg, dist=dist if world > 1 else None, replicate=rep)
     else:  # shards generated in place (paper-scale shapes: no [N x D] matrix in vertex order in HBM)
         dp.build_feature_cache_synth(order, cap, SEED, kg=kg, j=rank % kg, dist=dist if world > 1 else None,
-                                     keep_backing=feat_host)
+                                     keep_backing=feat_host, replicate=rep)
     topo_cap = 0
     if topo_host:
         # hot-vertex topology cache in HBM (GraphCache, storage/graph_storage.cu:76-111), ranked by the presampled
@@ -485,7 +488,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"{shape['name']}-shaped synthetic graph (BASELINE.json " + {"products": "configs[1]", "paper100m": "configs[2] shape", "ukunion": "configs[3] shape, 128-d", "clueweb": "configs[4] shape"}[shape["name"]] + ")",
                        "num_nodes": N, "num_edges": E, "feature_dim": D, "fanout": fanout, "batch": B,
-                       "scale": args.scale, "cache": f"Kc={world // kg},Kg={kg}: feature table interleaved by hotness rank over {kg} GPU(s) per clique"
+                       "scale": args.scale, "cache": f"Kc={world // kg},Kg={kg}: feature table interleaved by hotness rank over {kg} GPU(s) per clique" + (f", hottest {rep} rows replicated on every GPU" if rep else "")
                                 + (f", hottest {args.cache_ratio:.3f} of the rows in HBM ({cap} rows/GPU), the rest in pinned host memory (UVA)" if feat_host else ", fully HBM-cached")
                                 + (f"; topology in pinned host memory (UVA) with the hottest {args.topo_cache_ratio:.3f} of the adjacency lists cached in HBM ({topo_cap} rows/GPU)" if topo_host else "; topology replicated in HBM"),
                        "feature_cache_ratio": args.cache_ratio, "topology": args.topo, "topology_cache_ratio": args.topo_cache_ratio if topo_host else None,
@@ -631,6 +634,8 @@ def main():
                     help="gather launches per batch: 0 one per lookup op, 1 seeds ride with hop 1, 2 single gather")
     ap.add_argument("--kg", type=int, default=0, help="GPUs sharing one partitioned cache (0 = auto by capacity)")
     ap.add_argument("--cache-gb", type=float, default=100.0, help="per-GPU feature-cache budget used by --kg auto")
+    ap.add_argument("--replicate-ratio", type=float, default=0.0,
+                    help="with --kg > 1: fraction of the rows (hottest first) stored on every GPU instead of partitioned")
     ap.add_argument("--cache-ratio", type=float, default=1.0,
                     help="fraction of the feature rows cached in HBM across the clique; < 1 puts the backing matrix in "
                          "pinned host memory and misses are read over PCIe (UVA)")

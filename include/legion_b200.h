@@ -278,6 +278,15 @@ int lg_place_topology(lg_stream_t stream, const int32_t* order, int32_t cap, int
 int lg_fill_feature_shard(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg,
                           int32_t j, int32_t dim, int64_t num_nodes, const float* backing,
                           float* shard);
+/* Hybrid placement (no reference counterpart: a B200 has room to spare, Legion's GPUs did not): the `rep` hottest ranks
+ * are stored on EVERY GPU of the clique (rows 0..rep-1 of each shard) and resolve to the reader's own part `j` — local
+ * HBM reads for the head of the distribution instead of (Kg-1)/Kg peer reads — and the ranks after them are interleaved
+ * over the parts below row `rep` exactly like lg_place_features / lg_fill_feature_shard do from row 0 (rep = 0 is the
+ * reference placement).  Every GPU builds its own directory.  Rows cached per clique: rep + (cap-rep)*Kg. */
+int lg_place_features_hybrid(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg, int32_t rep, int32_t j,
+                             int64_t num_nodes, int32_t* directory);
+int lg_fill_feature_shard_hybrid(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg, int32_t rep, int32_t j,
+                                 int32_t dim, int64_t num_nodes, const float* backing, float* shard);
 /* GraphCache (storage/graph_storage.cu:76-111; graph_storage_impl.cuh:33-53), two calls:
  * counts -> shard_indptr[cap+1] (exclusive scan, shard_indptr[cap] = total edges), then fill. */
 int lg_topo_shard_indptr(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg,

@@ -35,6 +35,9 @@ int lg_synth_feature_rows(void* stream, const int32_t* ids, int64_t n, int32_t d
  * without a backing matrix); ranks >= num_nodes are zero-filled */
 int lg_synth_feature_shard(void* stream, const int32_t* order, int64_t cap, int32_t kg, int32_t j,
                            int32_t dim, int64_t num_nodes, uint64_t seed, float* shard);
+/* the same for the hybrid placement (lg_fill_feature_shard_hybrid): rows < rep hold ranks 0..rep-1 on every part */
+int lg_synth_feature_shard_hybrid(void* stream, const int32_t* order, int64_t cap, int32_t kg, int64_t rep, int32_t j,
+                                  int32_t dim, int64_t num_nodes, uint64_t seed, float* shard);
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,8 @@ _PROTOS = {
     "lg_place_features": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int64, vp]),
     "lg_place_topology": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp]),
     "lg_fill_feature_shard": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp, vp]),
+    "lg_place_features_hybrid": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp]),
+    "lg_fill_feature_shard_hybrid": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp, vp]),
     "lg_topo_shard_indptr": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp, vp]),
     "lg_topo_shard_fill": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp, vp]),
     "lg_fill_i32": (C.c_int, [vp, vp, C.c_int32, C.c_int64]),
@@ -125,6 +127,7 @@ _PROTOS = {
     "lg_synth_labels": (C.c_int, [vp, C.c_int64, C.c_int32, vp]),
     "lg_synth_feature_rows": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_uint64, vp]),
     "lg_synth_feature_shard": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, vp]),
+    "lg_synth_feature_shard_hybrid": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, vp]),
 }
 
 _lib = None

@@ -34,25 +34,35 @@ __global__ void fill_kernel(int32_t* v, int32_t x, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     v[i] = x;
 }
-// InitPair / InitIndexPair+InitOffsetPair followed by the hash insert, as one directory scatter
+// InitPair / InitIndexPair+InitOffsetPair followed by the hash insert, as one directory scatter.
+// Hybrid placement (rep > 0, features only): the rep hottest ranks live on EVERY GPU of the clique at row r and resolve to
+// the reader's own part (`self`); the ranks after them are interleaved over the parts like the reference's, below row rep.
 __global__ void place_kernel(const int32_t* __restrict__ order, int32_t cap, int32_t kg, int32_t part_base,
-                             int64_t num_nodes, int32_t* __restrict__ directory) {
-  const int64_t total = (int64_t)cap * kg;
+                             int64_t num_nodes, int32_t* __restrict__ directory, int32_t rep, int32_t self) {
+  const int64_t total = (int64_t)rep + (int64_t)(cap - rep) * kg;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total && r < num_nodes;
        r += (int64_t)gridDim.x * blockDim.x) {
-    int32_t part = (int32_t)(r % kg) + part_base;
-    directory[order[r]] = part * cap + (int32_t)(r / kg);
+    int32_t part, row;
+    if (r < rep) {
+      part = self;
+      row = (int32_t)r;
+    } else {
+      const int64_t q = r - rep;
+      part = (int32_t)(q % kg);
+      row = rep + (int32_t)(q / kg);
+    }
+    directory[order[r]] = (part + part_base) * cap + row;
   }
 }
 // FeatFillUp: one warp per row, 16-byte chunks when the row allows it
 __global__ void fill_feature_kernel(const int32_t* __restrict__ order, int32_t cap, int32_t kg, int32_t j,
                                     int32_t dim, int64_t num_nodes, const float* __restrict__ backing,
-                                    float* __restrict__ shard, int vec4) {
+                                    float* __restrict__ shard, int vec4, int32_t rep) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp; r < cap; r += n_warps) {
-    const int64_t rank = r * kg + j;
+    const int64_t rank = r < rep ? r : rep + (r - rep) * kg + j;  // replicated head, interleaved tail
     float* d = shard + r * dim;
     if (rank >= num_nodes) {
       for (int c = lane; c < dim; c += 32) d[c] = 0.f;
@@ -145,7 +155,17 @@ extern "C" int lg_place_features(lg_stream_t stream, const int32_t* order, int32
                                  int64_t num_nodes, int32_t* directory) {
   LG_REQUIRE(order && directory && cap > 0 && kg > 0, "lg_place_features: bad argument");
   LG_REQUIRE((int64_t)cap * kg < (1ll << 31), "lg_place_features: cap*kg overflows int32");
-  place_kernel<<<grid_for((int64_t)cap * kg), kBlock, 0, (cudaStream_t)stream>>>(order, cap, kg, 0, num_nodes, directory);
+  place_kernel<<<grid_for((int64_t)cap * kg), kBlock, 0, (cudaStream_t)stream>>>(order, cap, kg, 0, num_nodes, directory, 0, 0);
+  LG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lg_place_features_hybrid(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg, int32_t rep,
+                                        int32_t j, int64_t num_nodes, int32_t* directory) {
+  LG_REQUIRE(order && directory && cap > 0 && kg > 0 && rep >= 0 && rep <= cap && j >= 0 && j < kg,
+             "lg_place_features_hybrid: bad argument");
+  LG_REQUIRE((int64_t)cap * kg < (1ll << 31), "lg_place_features_hybrid: cap*kg overflows int32");
+  place_kernel<<<grid_for((int64_t)cap * kg), kBlock, 0, (cudaStream_t)stream>>>(order, cap, kg, 0, num_nodes, directory, rep, j);
   LG_LAUNCH_OK();
   return 0;
 }
@@ -155,7 +175,7 @@ extern "C" int lg_place_topology(lg_stream_t stream, const int32_t* order, int32
   LG_REQUIRE(order && directory && cap > 0 && kg > 0 && ki >= 0, "lg_place_topology: bad argument");
   LG_REQUIRE((int64_t)cap * kg * (ki + 1) < (1ll << 31), "lg_place_topology: packed location overflows int32");
   place_kernel<<<grid_for((int64_t)cap * kg), kBlock, 0, (cudaStream_t)stream>>>(order, cap, kg, ki * kg, num_nodes,
-                                                                                 directory);
+                                                                                 directory, 0, 0);
   LG_LAUNCH_OK();
   return 0;
 }
@@ -166,7 +186,18 @@ extern "C" int lg_fill_feature_shard(lg_stream_t stream, const int32_t* order, i
              "lg_fill_feature_shard: bad argument");
   int vec4 = (dim % 4 == 0) && (((uintptr_t)backing & 15) == 0) && (((uintptr_t)shard & 15) == 0);
   fill_feature_kernel<<<grid_for((int64_t)cap * 32), kBlock, 0, (cudaStream_t)stream>>>(order, cap, kg, j, dim, num_nodes,
-                                                                                      backing, shard, vec4);
+                                                                                      backing, shard, vec4, 0);
+  LG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lg_fill_feature_shard_hybrid(lg_stream_t stream, const int32_t* order, int32_t cap, int32_t kg, int32_t rep,
+                                            int32_t j, int32_t dim, int64_t num_nodes, const float* backing, float* shard) {
+  LG_REQUIRE(order && backing && shard && cap > 0 && kg > 0 && rep >= 0 && rep <= cap && j >= 0 && j < kg && dim > 0,
+             "lg_fill_feature_shard_hybrid: bad argument");
+  int vec4 = (dim % 4 == 0) && (((uintptr_t)backing & 15) == 0) && (((uintptr_t)shard & 15) == 0);
+  fill_feature_kernel<<<grid_for((int64_t)cap * 32), kBlock, 0, (cudaStream_t)stream>>>(order, cap, kg, j, dim, num_nodes,
+                                                                                      backing, shard, vec4, rep);
   LG_LAUNCH_OK();
   return 0;
 }

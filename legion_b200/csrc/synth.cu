@@ -51,13 +51,13 @@ __global__ void features_kernel(int64_t row0, int64_t rows, int32_t dim, u64 see
 }
 // rows addressed through an id list: out[r, c] = feat(idmap(r), c)
 __global__ void feature_rows_kernel(const int32_t* __restrict__ ids, int64_t stride, int64_t offset, int64_t id_count,
-                                    int64_t rows, int32_t dim, u64 seed, float* __restrict__ out) {
+                                    int64_t rows, int32_t dim, u64 seed, float* __restrict__ out, int64_t rep = 0) {
   const u64 s3 = seed ^ 0xFEA7FEA7FEA7FEA7ull;
   const int64_t total = rows * dim;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / dim;
     const int32_t c = (int32_t)(i - r * dim);
-    const int64_t k = r * stride + offset;
+    const int64_t k = r < rep ? r : rep + (r - rep) * stride + offset;  // rep: replicated head of a hybrid shard
     const int32_t v = (k < id_count) ? ids[k] : -1;
     uint32_t bits = 0;
     if (v >= 0) bits = (uint32_t)hash2(s3, (u64)((int64_t)v * dim + c)) & 0xBFFFFFFFu;
@@ -120,6 +120,14 @@ extern "C" int lg_synth_feature_shard(void* stream, const int32_t* order, int64_
                                       int64_t num_nodes, uint64_t seed, float* shard) {
   LG_REQUIRE(order && shard && cap > 0 && kg > 0 && j >= 0 && j < kg && dim > 0, "lg_synth_feature_shard: bad argument");
   feature_rows_kernel<<<grid_for(cap * dim), 256, 0, (cudaStream_t)stream>>>(order, kg, j, num_nodes, cap, dim, seed, shard);
+  LG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int lg_synth_feature_shard_hybrid(void* stream, const int32_t* order, int64_t cap, int32_t kg, int64_t rep, int32_t j,
+                                             int32_t dim, int64_t num_nodes, uint64_t seed, float* shard) {
+  LG_REQUIRE(order && shard && cap > 0 && kg > 0 && rep >= 0 && rep <= cap && j >= 0 && j < kg && dim > 0,
+             "lg_synth_feature_shard_hybrid: bad argument");
+  feature_rows_kernel<<<grid_for(cap * dim), 256, 0, (cudaStream_t)stream>>>(order, kg, j, num_nodes, cap, dim, seed, shard, rep);
   LG_LAUNCH_OK();
   return 0;
 }

@@ -259,17 +259,18 @@ class DataPath:
         torch.cuda.current_stream().synchronize()
         return order, sorted_h
 
-    def build_feature_cache(self, order, cap, kg=1, j=0, peers=None, dist=None):
+    def build_feature_cache(self, order, cap, kg=1, j=0, peers=None, dist=None, replicate=0):
         """FillUp feature part (cache/cache.cu:565-602).  kg > 1: this process fills shard j and maps the
-        others through CUDA IPC (`dist` = torch.distributed module, already initialised)."""
+        others through CUDA IPC (`dist` = torch.distributed module, already initialised).  replicate = rows at the
+        head of every shard that hold the hottest ranks on EVERY part (hybrid placement, lg_place_features_hybrid)."""
         st = self._stream()
         dev = f"cuda:{self.device}"
         directory = torch.empty(self.N, dtype=I32, device=dev)
         check(self.L.lg_fill_i32(st, _ptr(directory), capi.CACHEMISS_FLAG, self.N))
-        check(self.L.lg_place_features(st, _ptr(order), cap, kg, self.N, _ptr(directory)))
+        check(self.L.lg_place_features_hybrid(st, _ptr(order), cap, kg, replicate, j, self.N, _ptr(directory)))
         raw = self._shard_alloc(cap * self.dim * 4, kg)
-        check(self.L.lg_fill_feature_shard(st, _ptr(order), cap, kg, j, self.dim, self.N, C.c_void_p(self._backing),
-                                           C.c_void_p(raw.ptr)))
+        check(self.L.lg_fill_feature_shard_hybrid(st, _ptr(order), cap, kg, replicate, j, self.dim, self.N,
+                                                  C.c_void_p(self._backing), C.c_void_p(raw.ptr)))
         torch.cuda.current_stream().synchronize()
         shard_ptrs = [0] * kg
         shard_ptrs[j] = raw.ptr
@@ -281,16 +282,17 @@ class DataPath:
         self.feat_shard = raw
         return directory
 
-    def build_feature_cache_synth(self, order, cap, seed, kg=1, j=0, dist=None, keep_backing=False):
+    def build_feature_cache_synth(self, order, cap, seed, kg=1, j=0, dist=None, keep_backing=False, replicate=0):
         """as build_feature_cache, but the shard is generated in place from the synthetic feature function
         (include/legion_b200_synth.h): no [N x D] backing matrix exists anywhere (paper-scale shapes)"""
         st = self._stream()
         dev = f"cuda:{self.device}"
         directory = torch.empty(self.N, dtype=I32, device=dev)
         check(self.L.lg_fill_i32(st, _ptr(directory), capi.CACHEMISS_FLAG, self.N))
-        check(self.L.lg_place_features(st, _ptr(order), cap, kg, self.N, _ptr(directory)))
+        check(self.L.lg_place_features_hybrid(st, _ptr(order), cap, kg, replicate, j, self.N, _ptr(directory)))
         raw = self._shard_alloc(cap * self.dim * 4, kg)
-        check(self.L.lg_synth_feature_shard(st, _ptr(order), cap, kg, j, self.dim, self.N, seed, C.c_void_p(raw.ptr)))
+        check(self.L.lg_synth_feature_shard_hybrid(st, _ptr(order), cap, kg, replicate, j, self.dim, self.N, seed,
+                                                   C.c_void_p(raw.ptr)))
         torch.cuda.current_stream().synchronize()
         shard_ptrs = [0] * kg
         shard_ptrs[j] = raw.ptr

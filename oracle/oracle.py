@@ -55,6 +55,8 @@ def lib():
     L.lgo_place_features.argtypes = [i32p, C.c_int32, C.c_int32, C.c_int64, i32p]
     L.lgo_place_topology.argtypes = [i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, i32p]
     L.lgo_fill_feature_shard.argtypes = [i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, f32p, f32p]
+    L.lgo_place_features_hybrid.argtypes = [i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, i32p]
+    L.lgo_fill_feature_shard_hybrid.argtypes = [i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, f32p, f32p]
     L.lgo_fill_topo_shard.argtypes = [i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, i64p, i32p, i64p,
                                       C.c_void_p]
     L.lgo_feature_lookup.argtypes = [i32p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32,
@@ -185,6 +187,21 @@ def place_features(order, cap, kg, N):
     d = np.empty(N, np.int32)
     lib().lgo_place_features(np.ascontiguousarray(order, np.int32), cap, kg, N, d)
     return d
+
+
+def place_features_hybrid(order, cap, kg, rep, j, N):
+    """lg_place_features_hybrid: the rep hottest ranks replicated on every part, the rest interleaved below them"""
+    d = np.empty(N, np.int32)
+    lib().lgo_place_features_hybrid(np.ascontiguousarray(order, np.int32), cap, kg, rep, j, N, d)
+    return d
+
+
+def fill_feature_shard_hybrid(order, cap, kg, rep, j, backing):
+    N, dim = backing.shape
+    sh = np.empty((cap, dim), np.float32)
+    lib().lgo_fill_feature_shard_hybrid(np.ascontiguousarray(order, np.int32), cap, kg, rep, j, dim, N,
+                                        np.ascontiguousarray(backing, np.float32).reshape(-1), sh.reshape(-1))
+    return sh
 
 
 def place_topology(order, cap, kg, ki, N):

@@ -98,6 +98,54 @@ def test_cache_build_matches_oracle(oracle):
             assert np.array_equal(six.cpu().numpy()[: int(w_sip[-1])], w_six)
 
 
+@pytest.mark.parametrize("variant", [capi.GATHER_LDG, capi.GATHER_TMA])
+def test_hybrid_placement_gather(oracle, variant):
+    """hybrid placement (replicated head + interleaved tail): directory and shards equal the oracle's for every part, and
+    a gather through part j's directory returns the right rows with the head counted as local reads"""
+    indptr, indices = small_graph(2500, 9.0, 120)
+    N = len(indptr) - 1
+    dim = 100
+    feat = synth.features(0, N, dim, 8)
+    rig = Rig(indptr, indices, feat, [2], 8)
+    rng = np.random.default_rng(5)
+    hot_np = rng.integers(0, 1000, N).astype(np.uint64)
+    order, _ = rig.dp.rank_hotness(torch.from_numpy(hot_np.astype(np.int64)).to(rig.dev))
+    w_order, _ = oracle.hotness_rank(hot_np)
+    L, st = rig.dp.L, rig.dp._stream()
+    kg, cap, rep = 4, 300, 120
+    shards = []
+    for j in range(kg):
+        sh = torch.empty((cap, dim), dtype=torch.float32, device=rig.dev)
+        capi.check(L.lg_fill_feature_shard_hybrid(st, order.data_ptr(), cap, kg, rep, j, dim, N, rig.dp._backing, sh.data_ptr()))
+        assert np.array_equal(sh.cpu().numpy().view(np.uint32), oracle.fill_feature_shard_hybrid(w_order, cap, kg, rep, j, feat).view(np.uint32))
+        shards.append(sh)
+    ids = rng.integers(0, N, 6000).astype(np.int32)
+    d_ids = torch.from_numpy(ids).to(rig.dev)
+    cached_rank = np.full(N, N, np.int64)
+    cached_rank[w_order] = np.arange(N)
+    for j in (0, 2):
+        d = torch.empty(N, dtype=torch.int32, device=rig.dev)
+        capi.check(L.lg_fill_i32(st, d.data_ptr(), -2, N))
+        capi.check(L.lg_place_features_hybrid(st, order.data_ptr(), cap, kg, rep, j, N, d.data_ptr()))
+        assert np.array_equal(d.cpu().numpy(), oracle.place_features_hybrid(w_order, cap, kg, rep, j, N))
+        fc = capi.FeatureCache()
+        fc.n_parts, fc.shard_rows, fc.dim, fc.num_nodes = kg, cap, dim, N
+        for k in range(kg):
+            fc.shard[k] = shards[k].data_ptr()
+        fc.backing = rig.dp._backing
+        fc.directory = d.data_ptr()
+        out = torch.empty((len(ids), dim), dtype=torch.float32, device=rig.dev)
+        tiers = torch.zeros(3, dtype=torch.int64, device=rig.dev)
+        capi.check(L.lg_gather_rows(st, C.byref(fc), d_ids.data_ptr(), len(ids), out.data_ptr(), j, variant, tiers.data_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), feat[ids].view(np.uint32))
+        r = cached_rank[ids]
+        tail = (r >= rep) & (r < rep + (cap - rep) * kg)
+        want_local = int((r < rep).sum() + (tail & ((r - rep) % kg == j)).sum())
+        want_peer = int((tail & ((r - rep) % kg != j)).sum())
+        assert tiers.cpu().tolist() == [want_local, want_peer, len(ids) - want_local - want_peer]
+
+
 def test_synth_device_generator_matches_numpy():
     L = capi.load()
     N, dmin, dmax, seed = 30000, 5.25, 700, 0x1e910
