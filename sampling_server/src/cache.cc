@@ -110,11 +110,25 @@ void UnifiedCache::CostModel(int, FeatureStorage* feature, GraphStorage* graph, 
   }
 }
 
+// LEGION_REPLICATE_RATIO=r (default 0 = the reference placement): the first r * node_capacity rows of every feature
+// shard hold the hottest ranks on EVERY GPU of the clique (hybrid placement, lg_place_features_hybrid); only the ranks
+// after them are interleaved.  Same shard size, fewer distinct rows cached, local reads for the head of the order.
+static int32_t ReplicatedRows(int32_t ncap, int32_t kg) {
+  const char* e = std::getenv("LEGION_REPLICATE_RATIO");
+  if (!e || kg <= 1) return 0;
+  double r = std::atof(e);
+  if (r <= 0) return 0;
+  if (r > 1) r = 1;
+  return (int32_t)(r * ncap);
+}
+
 void UnifiedCache::FillUp(int, FeatureStorage* feature, GraphStorage* graph) {
   const int64_t n = feature->TotalNodeNum();
   const int32_t dim = feature->GetFloatFeatureLen();
   for (int32_t i = 0; i < Kc_; i++) {
     const int32_t ncap = node_capacity_[i], ecap = edge_capacity_[i];
+    const int32_t rep = ReplicatedRows(ncap, Kg_);
+    if (rep > 0) std::cout << "Replicated feature rows: " << rep << " of " << ncap << " per GPU on Clique: " << i << std::endl;
     std::vector<float*> shard(Kg_);
     std::vector<int64_t*> sip(Kg_);
     std::vector<int32_t*> six(Kg_);
@@ -122,7 +136,7 @@ void UnifiedCache::FillUp(int, FeatureStorage* feature, GraphStorage* graph) {
       const int32_t dev = i * Kg_ + j;
       LGCHECK(lg_set_device(dev));
       shard[j] = (float*)DevAlloc((int64_t)ncap * dim * 4, false);
-      LGCHECK(lg_fill_feature_shard(nullptr, QF_[i], ncap, Kg_, j, dim, n, feature->GetAllFloatFeature(), shard[j]));
+      LGCHECK(lg_fill_feature_shard_hybrid(nullptr, QF_[i], ncap, Kg_, rep, j, dim, n, feature->GetAllFloatFeature(), shard[j]));
       sip[j] = (int64_t*)DevAlloc((int64_t)(ecap + 1) * 8, false);
       LGCHECK(lg_topo_shard_indptr(nullptr, QT_[i], ecap, Kg_, j, n, graph->GetCSRNodeIndexCPU(), sip[j]));
       int64_t total = 0;
@@ -138,7 +152,7 @@ void UnifiedCache::FillUp(int, FeatureStorage* feature, GraphStorage* graph) {
       LGCHECK(lg_set_device(dev));
       auto* fdir = (int32_t*)DevAlloc(n * 4, false);
       LGCHECK(lg_fill_i32(nullptr, fdir, CACHEMISS_FLAG, n));
-      LGCHECK(lg_place_features(nullptr, QF_[i], ncap, Kg_, n, fdir));
+      LGCHECK(lg_place_features_hybrid(nullptr, QF_[i], ncap, Kg_, rep, j, n, fdir));
       auto* tdir = (int32_t*)DevAlloc(n * 4, false);
       LGCHECK(lg_fill_i32(nullptr, tdir, CACHEMISS_FLAG, n));
       LGCHECK(lg_place_topology(nullptr, QT_[i], ecap, Kg_, 0, n, tdir));  // parts are clique-local slots

@@ -91,10 +91,12 @@ def test_server_to_trainer_handoff(oracle, tmp_path, fanout, cache_bytes):
             proc.kill()
 
 
-@pytest.mark.parametrize("gpus,agg_mode,cache_bytes", [(2, "1.0", 150_000), (2, "0.0", 10_000_000)])
-def test_server_multi_gpu_handoff(oracle, tmp_path, gpus, agg_mode, cache_bytes):
+@pytest.mark.parametrize("gpus,agg_mode,cache_bytes,replicate", [(2, "1.0", 150_000, "0"), (2, "0.0", 10_000_000, "0"),
+                                                                   (2, "1.0", 150_000, "0.4")])
+def test_server_multi_gpu_handoff(oracle, tmp_path, gpus, agg_mode, cache_bytes, replicate):
     """one server process, one thread per GPU (engine/server.cu:122-130), partitioned (Kg=2) or replicated (Kg=1) cache
-    read over cudaDeviceEnablePeerAccess; one trainer process per GPU (rank == device) checks every batch"""
+    read over cudaDeviceEnablePeerAccess — also with the hybrid placement (LEGION_REPLICATE_RATIO: the head of every
+    shard replicated on both GPUs); one trainer process per GPU (rank == device) checks every batch"""
     from legion_b200 import dataset, synth
     if torch.cuda.device_count() < gpus:
         pytest.skip(f"needs >= {gpus} GPUs")
@@ -110,8 +112,8 @@ def test_server_multi_gpu_handoff(oracle, tmp_path, gpus, agg_mode, cache_bytes)
     for f in os.listdir("/dev/shm"):
         if f.startswith("sem.sem_") or f == "simpleIPCshm":
             os.unlink(os.path.join("/dev/shm", f))
-    proc = subprocess.Popen([BIN, str(gpus), agg_mode], cwd=cwd, env=dict(os.environ, LEGION_SEED=str(seed)), stdout=subprocess.PIPE,
-                            stderr=subprocess.STDOUT, text=True)
+    proc = subprocess.Popen([BIN, str(gpus), agg_mode], cwd=cwd, env=dict(os.environ, LEGION_SEED=str(seed), LEGION_REPLICATE_RATIO=replicate),
+                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     consumers = []
     try:
         _wait_ready(proc)
