@@ -140,21 +140,26 @@ int lg_sampler_set_overlap(lg_sampler* s, int32_t mode);
  * the last hop's relabel kernel also releases the position map (lg_io_complete then has nothing left to launch):
  * two kernel launches less per batch, same final buffers and counters. */
 int lg_sampler_set_lazy_relabel(lg_sampler* s, int32_t mode);
+/* Seed offset of the clipped tail batch of a set (batch_size * (counter+1) > total_cap).  LG_TAIL_EXACT (default): the
+ * batch starts at batch_size * counter — the true tail of the set.  LG_TAIL_REFERENCE: it starts at clipped_size * counter,
+ * what the reference computes (engine/operator_impl.cu:159-162 pass the clipped size as the kernel's batch_size, :40,:44
+ * multiply it by the counter): with the server's valid/test batch size ceil(n/steps) the last eval batch re-reads seeds
+ * from the middle of the set and the real tail is never served.  Full batches are identical in both modes. */
+#define LG_TAIL_EXACT 0
+#define LG_TAIL_REFERENCE 1
+int lg_sampler_set_tail_mode(lg_sampler* s, int32_t mode);
 /* make `stream` wait until the batch last produced into `batch` is complete (mode 2; no-op otherwise) */
 int lg_batch_wait(lg_sampler* s, lg_stream_t stream, const lg_batch* batch);
-/* sticky overflow status (0 ok, 1 ids overflow, 3 cache miss without a backing matrix, 2 features buffer too small — the reference
- * sizes it 1.2 x presampled max without a bound check, engine/server.cu:277).  Synchronises. */
+/* sticky status (0 ok, 1 ids overflow, 2 features buffer too small — the reference sizes it 1.2 x presampled max without a
+ * bound check, engine/server.cu:277 —, 3 cache miss without a backing matrix, 4 edge_dst holds a vertex id outside
+ * [0, num_nodes): the reference drops the edge when the id is negative, engine/operator_impl.cu:244, and reads out of
+ * bounds otherwise; here the batch is flagged invalid and stays memory-safe).  Synchronises. */
 int lg_sampler_status(lg_sampler* s, lg_stream_t stream, int32_t* host_status);
 /* the same copy without the synchronisation: `pinned_host_status` (page-locked) holds the flag once the work enqueued on
  * `stream` so far has completed — a pipelined host reads it after the event it waits for anyway */
 int lg_sampler_status_async(lg_sampler* s, lg_stream_t stream, int32_t* pinned_host_status);
 
-/* diagnostics: per-tile phase timestamps of the sampler kernels (globaltimer ns, clock64) written to a device
- * buffer of lg_debug_trace_words() u64 words, layout [(hop-1)*2 + kernel][tile < 2048][phase < 8][2]; NULL = off */
-/* diagnostics: `ctas` x `threads` spinning for `cycles` SM clocks without touching memory */
-int lg_debug_spin(lg_stream_t stream, int32_t ctas, int32_t threads, int64_t cycles);
-int lg_debug_set_trace(lg_sampler* s, unsigned long long* device_buf);
-int64_t lg_debug_trace_words(void);
+/* diagnostics (kernel-launch counter, phase traces, spin kernel) live in legion_b200_debug.h, not in this ABI */
 
 /* ---- the five operator bodies (engine/operator_impl.cuh:11-63) ---- */
 

@@ -15,6 +15,7 @@ CACHEMISS_FLAG = -2
 RNG_MINSTD, RNG_PHILOX = 0, 1
 GATHER_AUTO, GATHER_LDG, GATHER_TMA = 0, 1, 2
 TRAINMODE, VALIDMODE, TESTMODE = 0, 1, 2
+TAIL_EXACT, TAIL_REFERENCE = 0, 1
 
 vp = C.c_void_p
 
@@ -53,8 +54,11 @@ _PROTOS = {
     "lg_sampler_dedup_layout": (C.c_int32, [vp]),
     "lg_sampler_set_gather_variant": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_overlap": (C.c_int, [vp, C.c_int32]),
+    "lg_sampler_set_tail_mode": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_lazy_relabel": (C.c_int, [vp, C.c_int32]),
     "lg_sampler_set_gather_fusion": (C.c_int, [vp, C.c_int32]),
+    # include/legion_b200_debug.h
+    "lg_debug_launch_count": (C.c_longlong, [C.c_int32]),
     "lg_debug_spin": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int64]),
     "lg_debug_set_trace": (C.c_int, [vp, vp]),
     "lg_debug_trace_words": (C.c_int64, []),

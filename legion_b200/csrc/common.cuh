@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "../../include/legion_b200.h"
+#include "../../include/legion_b200_debug.h"
 
 int lg_set_error(const char* fmt, ...);
 int lg_l2_hints();  // LG_L2_HINTS bitmask (see the L2 eviction-priority helpers below)
@@ -14,12 +15,14 @@ int lg_pdl();  // LG_PDL: -1 unset (per-handle default: on for the dense positio
                // bit 1 except the position-map release; bit 2 except batch_generate
 int lg_chain_carveout();  // LG_CARVEOUT: preferred shared-memory carve-out (%) of the sampler-chain kernels, -1 = driver's choice
 void lg_apply_carveout(const void* kernel);
+void lg_count_launch();  // lg_debug_launch_count
 
 // kernel launch of the per-batch chain: cudaLaunchKernelEx, with the PDL attribute when enabled
 template <typename... KArgs, typename... Args>
 static inline cudaError_t lg_launch_opt(bool allow_pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem,
                                         cudaStream_t st, Args... args) {
   if (lg_chain_carveout() >= 0) lg_apply_carveout((const void*)kernel);
+  lg_count_launch();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -41,7 +44,11 @@ static inline cudaError_t lg_launch_opt(bool allow_pdl, void (*kernel)(KArgs...)
     if (e_ != cudaSuccess)                                                                  \
       return lg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
   } while (0)
-#define LG_LAUNCH_OK() LG_CUDA(cudaGetLastError())
+#define LG_LAUNCH_OK()        \
+  do {                        \
+    lg_count_launch();        \
+    LG_CUDA(cudaGetLastError()); \
+  } while (0)
 #define LG_REQUIRE(cond, ...)                      \
   do {                                             \
     if (!(cond)) return lg_set_error(__VA_ARGS__); \

@@ -46,6 +46,13 @@ void lg_apply_carveout(const void* kernel) {  // once per kernel
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, lg_chain_carveout());
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void lg_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long lg_debug_launch_count(int32_t reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
 int lg_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -206,7 +206,7 @@ __device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* s_re
 struct BatchGenArgs {
   const int32_t* all_ids;
   const int32_t* all_labels;
-  int32_t total_cap, size, counter, hop_num;
+  int32_t total_cap, size, stride, counter, hop_num;
   int32_t* ids;
   int32_t* labels;
   int32_t* nc;
@@ -231,7 +231,10 @@ __device__ __forceinline__ void batch_generate_body(const BatchGenArgs& g, int32
     g.ec[t] = 0;
   }
   for (int32_t idx = t; idx < g.size; idx += n_threads) {
-    const long long pos = (long long)g.size * g.counter + idx;  // the reference strides by the clipped size (:40,:44,:162)
+    // offset of the batch in the set: batch_size * counter.  The reference passes the CLIPPED size of a tail batch as the
+    // kernel's batch_size (:159-162), so its last batch re-reads seeds from the middle of the set (:40,:44);
+    // lg_sampler_set_tail_mode(LG_TAIL_REFERENCE) keeps that stride (g.stride = g.size)
+    const long long pos = (long long)g.stride * g.counter + idx;
     if (pos >= g.total_cap) {
       g.ids[idx] = -1;
       g.labels[idx] = -1;
@@ -274,7 +277,8 @@ struct SampleHop {  // what changes from hop to hop
   HopState* hs;
   int32_t hop;
   int32_t fanout;
-  uint32_t fanout_magic;  // ceil(2^32 / fanout): slot / fanout as one multiply-high (slot < 2^16)
+  uint32_t fanout_magic;  // ceil(2^32 / fanout): k / fanout as one multiply-high, exact for every k < 256 * fanout while
+                          // fanout <= 4096 (k * (magic * fanout - 2^32) < 2^32); 0 = larger fan-out, plain division
   int32_t relabel_prev;   // also write the previous hop's agg_src (its construct_graph) from the position map
 };
 struct SampleArgs {
@@ -287,6 +291,7 @@ struct SampleArgs {
   int32_t* ec;
   DedupMap map;
   u64* edge_hot;
+  int32_t* status;        // sticky status word of the handle (4 = edge_dst holds an id outside [0, num_nodes))
   int32_t precheck;       // DENSE: L1-cached look at the map word before the RED.MIN (LG_RED_PRECHECK)
   uint32_t batch_id, stream_id, k0, k1;
   int32_t l2;  // lg_l2_hints()
@@ -411,13 +416,20 @@ __device__ __forceinline__ bool sample_tile(const SampleArgs& a, const SampleHop
       const int k = k0 + u * kBlock;
       p[u] = -1;
       if (k < n_slots) {
-        const int t = (c == 1) ? k : (int)__umulhi((uint32_t)k, h.fanout_magic);
+        const int t = (c == 1) ? k : (h.fanout_magic ? (int)__umulhi((uint32_t)k, h.fanout_magic) : k / c);
         const int j = k - t * c;
         if (j < s_cnt[t]) {  // :232  neighbor_offset >= col_size -> none
           const uint32_t slot = (uint32_t)(i0 + t) * (uint32_t)c + (uint32_t)j;
           const int32_t pick =
               pick_neighbor<RNG>(slot, s_deg[t], (uint32_t)h.hop, a.batch_id, a.stream_id, a.k0, a.k1);
           w[u] = ld_nc_s32_hint(s_indices[t] + s_start[t] + pick, once);  // :240-242
+          // the reference drops an edge whose neighbour id is negative (:244) and reads out of bounds for ids >= N; here
+          // the edge positions are fixed before the pick is read, so such a dataset is flagged (sticky status 4) and the
+          // slot falls back to vertex 0 — every later access stays in bounds, the batch is marked invalid
+          if ((uint32_t)w[u] >= (uint32_t)a.topo.num_nodes) {
+            *a.status = 4;
+            w[u] = 0;
+          }
           p[u] = base + s_off[t] + j;
           fl[u] = s_flocal[t];
         }
@@ -939,6 +951,12 @@ extern "C" int64_t lg_num_ids(int32_t batch_size, const int32_t* fanout, int32_t
   return tot;
 }
 
+// see SampleHop::fanout_magic
+static uint32_t fanout_magic(int32_t fanout) {
+  if (fanout > 4096) return 0u;
+  return (uint32_t)(((1ull << 32) + (uint64_t)fanout - 1) / (uint64_t)fanout);
+}
+
 static int pick_tile_f(int64_t frontier_max) {
   // a tile is one CTA: prefer many small tiles for short frontiers (latency), 256-entry tiles for long ones
   if (frontier_max >= 128ll * kSMs * 4) return 256;
@@ -1146,6 +1164,13 @@ extern "C" int lg_sampler_set_lazy_relabel(lg_sampler* s, int32_t mode) {
   return 0;
 }
 
+extern "C" int lg_sampler_set_tail_mode(lg_sampler* s, int32_t mode) {
+  LG_REQUIRE(s, "null sampler");
+  LG_REQUIRE(mode == LG_TAIL_EXACT || mode == LG_TAIL_REFERENCE, "tail mode %d", mode);
+  s->tail_reference = mode;
+  return 0;
+}
+
 extern "C" int lg_sampler_set_overlap(lg_sampler* s, int32_t mode) {
   LG_REQUIRE(s, "null sampler");
   LG_REQUIRE(mode >= 0 && mode <= 2, "overlap mode %d", mode);
@@ -1254,8 +1279,9 @@ static int32_t clipped_batch_size(int32_t total_cap, int32_t batch_size, int32_t
   return size < 0 ? 0 : size;
 }
 static BatchGenArgs batch_gen_args(const lg_sampler* s, const int32_t* all_ids, const int32_t* all_labels, int32_t total_cap,
-                                   int32_t size, int32_t counter, const lg_batch* b) {
+                                   int32_t size, int32_t batch_size, int32_t counter, const lg_batch* b) {
   BatchGenArgs g;
+  g.stride = s->tail_reference ? size : batch_size;
   g.all_ids = all_ids;
   g.all_labels = all_labels;
   g.total_cap = total_cap;
@@ -1291,7 +1317,7 @@ extern "C" int lg_batch_generate(lg_sampler* s, lg_stream_t stream_, const int32
     LG_CUDA(lg_launch_opt(pdl_on(s, 4), release_kernel, kSMs * 8, kBlock, 0, st, release_args(s, b)));
   s->table_clean = 0;
   const int32_t size = clipped_batch_size(total_cap, batch_size, counter);
-  const BatchGenArgs g = batch_gen_args(s, all_ids, all_labels, total_cap, size, counter, b);
+  const BatchGenArgs g = batch_gen_args(s, all_ids, all_labels, total_cap, size, batch_size, counter, b);
   int grid = size > 0 ? (size + kBlock - 1) / kBlock : 1;
   // the kernel also zeroes the per-batch scan state (tickets + tile words): enough threads for one pass
   const int grid_small = (g.small_words + kBlock - 1) / kBlock;
@@ -1355,9 +1381,10 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   a.edge_hot = (u64*)edge_hotness;
   a.h.hop = hop;
   a.h.fanout = s->fanout[h];
-  a.h.fanout_magic = (uint32_t)(((1ull << 32) + (uint64_t)s->fanout[h] - 1) / (uint64_t)s->fanout[h]);
+  a.h.fanout_magic = fanout_magic(s->fanout[h]);
   a.h.relabel_prev = relabel_prev ? 1 : 0;
   a.precheck = sampler_tune().red_precheck;
+  a.status = s->status;
   a.batch_id = batch_id;
   a.stream_id = stream_id;
   a.k0 = (uint32_t)rng_seed;
@@ -1471,7 +1498,7 @@ static int launch_chain(lg_sampler* s, cudaStream_t st, const lg_topology* topo,
   ChainArgs c;
   memset(&c, 0, sizeof(c));
   const int32_t size = clipped_batch_size(p->total_cap, p->batch_size, p->counter);
-  c.gen = batch_gen_args(s, p->all_ids, p->all_labels, p->total_cap, size, p->counter, b);
+  c.gen = batch_gen_args(s, p->all_ids, p->all_labels, p->total_cap, size, p->batch_size, p->counter, b);
   SampleArgs& a = c.smp;
   a.topo = *topo;
   a.seed_local = nullptr;
@@ -1483,6 +1510,7 @@ static int launch_chain(lg_sampler* s, cudaStream_t st, const lg_topology* topo,
   a.map = map_of(s);
   a.edge_hot = nullptr;
   a.precheck = sampler_tune().red_precheck;
+  a.status = s->status;
   a.batch_id = p->batch_id;
   a.stream_id = p->stream_id;
   a.k0 = (uint32_t)p->rng_seed;
@@ -1502,7 +1530,7 @@ static int launch_chain(lg_sampler* s, cudaStream_t st, const lg_topology* topo,
   c.n_hops = s->n_hops;
   for (int h = 0; h < s->n_hops; h++) {
     c.fanout[h] = s->fanout[h];
-    c.magic[h] = (uint32_t)(((1ull << 32) + (uint64_t)s->fanout[h] - 1) / (uint64_t)s->fanout[h]);
+    c.magic[h] = fanout_magic(s->fanout[h]);
     c.tile_f[h] = s->sample_tile_f[h];
     c.rank_items[h] = s->rank_items[h];
     c.sample_state[h] = s->sample_state[h];
@@ -1610,7 +1638,7 @@ static int run_batch_host_impl(lg_sampler* s, lg_stream_t stream_, const lg_topo
   lg_batch_params q = *p;
   q.all_ids = d_seeds;
   q.all_labels = d_labels;
-  q.total_cap = p->batch_size + 1;  // strictly inside the set: no tail clipping
+  q.total_cap = p->batch_size;  // the staged seeds ARE the batch
   q.counter = 0;
   int rc = lg_run_batch(s, stream_, topo, cache, &q, b, nullptr);
   if (rc) return rc;

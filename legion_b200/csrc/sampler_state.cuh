@@ -45,7 +45,8 @@ struct lg_sampler {
   int32_t sample_tiles[LG_MAX_HOPS];
   int32_t sample_tile_f[LG_MAX_HOPS];
   int32_t rank_tiles[LG_MAX_HOPS];
-  int32_t* status;       // device int32: 1 = ids overflow, 2 = features buffer overflow
+  int32_t* status;       // device int32: 1 = ids overflow, 2 = features buffer overflow, 3 = miss without a backing matrix,
+                         // 4 = edge_dst holds an id outside [0, num_nodes)
   int32_t* gather_ticket;  // [2] dynamic tile claims of the gather (re-armed by the kernel itself)
   int32_t* pinned_seeds;
   // gather/sampling overlap inside lg_run_batch: the gather of hop h runs on `side` while hop h+1
@@ -56,6 +57,7 @@ struct lg_sampler {
   int32_t fuse_gathers;  // lg_run_batch: 0 = one gather per op (reference schedule); 1 = seeds' rows ride with hop 1;
                          // 2 = a single gather of all rows after the last hop
   int32_t lazy_relabel;  // op-by-op calls: hop h's construct_graph is finished by hop h+1 (lg_sampler_set_lazy_relabel)
+  int32_t tail_reference;  // lg_sampler_set_tail_mode: 1 = the tail batch strides by its clipped size like the reference
   int32_t overlap;  // 0 one stream, 1 fork/join inside a batch, 2 pipelined across batches (see lg_batch_wait)
   // pipelined mode: completion event of the last batch that used a given set of buffers
   struct Done {

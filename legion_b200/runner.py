@@ -109,6 +109,12 @@ class RawDeviceBuffer:
                 self.L.lg_ipc_close(C.c_void_p(self.ptr))
             self.ptr = None
 
+    def __del__(self):  # shards are tens of GB: a dropped cache must give its HBM back
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
 
 class MappedHostBuffer:
     """cudaHostAllocMapped memory (storage/storage_management.cu:108-109): numpy view + UVA device pointer."""
@@ -128,6 +134,12 @@ class MappedHostBuffer:
         if self.host_ptr:
             self.L.lg_host_free(C.c_void_p(self.host_ptr))
             self.host_ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class BatchBuffers:
@@ -192,6 +204,7 @@ class DataPath:
         self.topo = Topology()
         self.cache = FeatureCache()
         self._keep = []  # tensors referenced by the descriptors
+        self._cache_keep = []  # buffers owned by the current feature cache (shard, peer mappings)
         self.tier_rows = torch.zeros(3, dtype=torch.int64, device=f"cuda:{self.device}")
         self.local_part = 0
 
@@ -274,9 +287,9 @@ class DataPath:
         torch.cuda.current_stream().synchronize()
         shard_ptrs = [0] * kg
         shard_ptrs[j] = raw.ptr
-        self._keep.append(raw)
+        self._cache_keep = [raw]
         if kg > 1:
-            shard_ptrs = self._exchange(raw, cap * self.dim * 4, kg, j, dist)
+            shard_ptrs = self._exchange(raw, cap * self.dim * 4, kg, j, dist, keep=self._cache_keep)
         self.local_part = j
         self._set_cache(shard_ptrs, directory, cap)
         self.feat_shard = raw
@@ -296,9 +309,9 @@ class DataPath:
         torch.cuda.current_stream().synchronize()
         shard_ptrs = [0] * kg
         shard_ptrs[j] = raw.ptr
-        self._keep.append(raw)
+        self._cache_keep = [raw]
         if kg > 1:
-            shard_ptrs = self._exchange(raw, cap * self.dim * 4, kg, j, dist)
+            shard_ptrs = self._exchange(raw, cap * self.dim * 4, kg, j, dist, keep=self._cache_keep)
         self.local_part = j
         if not keep_backing:
             self._backing = 0
@@ -341,13 +354,24 @@ class DataPath:
             return RawDeviceBuffer.vmm(nbytes, self.device)
         return RawDeviceBuffer(nbytes, self.device)
 
-    def _exchange(self, raw, nbytes, kg, j, dist, nbytes_own=None):
+    def drop_feature_cache(self):
+        """release the current feature cache (shard, peer mappings, directory); every rank of the clique calls it
+        before any rank frees — the caller puts a barrier in front"""
+        self.feat_shard = None
+        self.feat_directory = None
+        for b in self._cache_keep:
+            b.free()
+        self._cache_keep = []
+        self._set_cache([], None, 0)
+
+    def _exchange(self, raw, nbytes, kg, j, dist, nbytes_own=None, keep=None):
         """one buffer per clique member -> the kg device pointers, own slot first-hand, peers mapped: VMM descriptors
         passed over AF_UNIX sockets, or (LG_SHARD_IPC=legacy) all-gathered CUDA IPC handles"""
         from .multigpu import exchange_fds, exchange_handles
         assert dist is not None and dist.is_initialized(), "multi-GPU cache needs torch.distributed"
         own_bytes = nbytes if nbytes is not None else nbytes_own
         self._xchg = getattr(self, "_xchg", 0) + 1
+        keep = self._keep if keep is None else keep
         ptrs = []
         if raw.owned == "vmm":
             import os
@@ -359,7 +383,7 @@ class DataPath:
                 else:
                     peer = RawDeviceBuffer.from_vmm_fd(fds[p], sizes[p], self.device)
                     os.close(fds[p])
-                    self._keep.append(peer)
+                    keep.append(peer)
                     ptrs.append(peer.ptr)
             dist.barrier()  # every import is done before anyone may close its exported descriptor
             os.close(raw.fd)
@@ -372,7 +396,7 @@ class DataPath:
             else:
                 h, nb = clique[p]
                 peer = RawDeviceBuffer.from_ipc(h, nb, self.device)
-                self._keep.append(peer)
+                keep.append(peer)
                 ptrs.append(peer.ptr)
         return ptrs
 
@@ -430,6 +454,10 @@ class DataPath:
     def set_overlap(self, mode):
         """0 one stream, 1 gathers overlap the next hop (joined per batch), 2 pipelined across batches"""
         check(self.L.lg_sampler_set_overlap(self.sampler, int(mode)))
+
+    def set_tail_mode(self, mode):
+        """capi.TAIL_EXACT (default) or capi.TAIL_REFERENCE (the reference's stride of the clipped tail batch)"""
+        check(self.L.lg_sampler_set_tail_mode(self.sampler, int(mode)))
 
     def set_gather_fusion(self, mode):
         """0 one gather per op, 1 seeds ride with hop 1, 2 single gather per batch"""

@@ -20,8 +20,8 @@ f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "legion_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("legion_oracle.c", "synth_oracle.c")]
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(_LIB_PATH) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, _LIB_PATH])
     return _LIB_PATH
 
@@ -73,6 +73,12 @@ def lib():
                                  i32p, i64p, i64p, i64p, i32p]
     L.lgo_index_select.argtypes = [f32p, C.c_int32, i32p, C.c_int64, f32p]
     L.lgo_block_csc.argtypes = [i32p, i32p, C.c_int64, C.c_int32, i32p, i32p, i32p]
+    L.lgo_synth_indptr.restype = C.c_int64
+    L.lgo_synth_indptr.argtypes = [C.c_int64, C.c_double, C.c_int32, C.c_uint64, i64p]
+    L.lgo_synth_indices.argtypes = [C.c_int64, i64p, C.c_uint64, i32p]
+    L.lgo_synth_features.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_uint64, f32p]
+    L.lgo_synth_feature_rows.argtypes = [i32p, C.c_int64, C.c_int32, C.c_uint64, f32p]
+    L.lgo_set_tail_exact.argtypes = [C.c_int32]
     L.lgo_num_threads.restype = C.c_int32
     L.lgo_set_num_threads.argtypes = [C.c_int32]
     _lib = L
@@ -119,8 +125,11 @@ class Oracle:
             pass
 
     def run_batch(self, all_ids, all_labels, batch_size, counter, rng_kind=RNG_PHILOX, seed=0, batch_id=0,
-                  stream_id=0, edge_hot=None, node_hot=None, per_hop=False):
+                  stream_id=0, edge_hot=None, node_hot=None, per_hop=False, tail_exact=True):
+        """tail_exact: the clipped tail batch starts at batch_size*counter (LG_TAIL_EXACT, the C ABI's default);
+        False = the reference's literal stride (engine/operator_impl.cu:159-162)"""
         L = self.L
+        L.lgo_set_tail_exact(1 if tail_exact else 0)
         all_ids = np.ascontiguousarray(all_ids, np.int32)
         all_labels = np.ascontiguousarray(all_labels, np.int32)
         n = self.num_ids
@@ -293,3 +302,28 @@ class DGLBaseline:
     def use_all_cores(self):
         self.L.lgo_set_num_threads(os.cpu_count() or 1)
         return self.threads()
+
+
+# ---- host-side twin of the synthetic dataset generator (oracle/synth_oracle.c) ----
+def synth_graph(n, dmin, dmax, seed):
+    """CSR of the synthetic graph, generated on the host cores (OpenMP); equals legion_b200.synth.graph bit for bit"""
+    L = lib()
+    indptr = np.empty(n + 1, np.int64)
+    e = int(L.lgo_synth_indptr(n, float(dmin), int(dmax), int(seed), indptr))
+    indices = np.empty(max(e, 1), np.int32)
+    L.lgo_synth_indices(n, indptr, int(seed), indices)
+    return indptr, indices[:e]
+
+
+def synth_features(row0, rows, dim, seed, out=None):
+    if out is None:
+        out = np.empty((rows, dim), np.float32)
+    lib().lgo_synth_features(int(row0), int(rows), int(dim), int(seed), out.reshape(-1))
+    return out
+
+
+def synth_feature_rows(ids, dim, seed):
+    ids = np.ascontiguousarray(ids, np.int32)
+    out = np.empty((len(ids), dim), np.float32)
+    lib().lgo_synth_feature_rows(ids, len(ids), int(dim), int(seed), out.reshape(-1))
+    return out

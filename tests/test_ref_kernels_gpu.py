@@ -241,3 +241,37 @@ def test_reference_placement_fill_and_gather_vs_ours(ref, oracle):
         capi.check(L.lg_gather_rows(st, C.byref(cache), d_ids[off:].data_ptr(), cnt, out[off:].data_ptr(), 0, variant, None))
         torch.cuda.synchronize()
         assert torch.equal(out.view(torch.int32), out_ref.view(torch.int32)), variant
+
+
+def test_reference_tail_batch_stride(ref, oracle):
+    """The clipped tail batch: the reference's own batch_generate (engine/operator_impl.cu:27-55 launched as :159-165)
+    equals ours in LG_TAIL_REFERENCE mode and the oracle's literal mode; LG_TAIL_EXACT (default) serves the true tail."""
+    indptr, indices = small_graph(3000, 10.0, 200)
+    N = len(indptr) - 1
+    ids, labels = make_sets(N, 0.1)  # 300 ids
+    fanout, B, counter = [5, 3], 128, 2  # 300 - 256 = 44 seeds left
+    rig = Rig(indptr, indices, synth.features(0, N, 8, 1), fanout, B)
+    d_ids, d_lab = rig.sets(ids, labels)
+    st = rig.dp._stream()
+    rs = RefState(N, rig.dp.num_ids, B)
+    tab = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    assert ref.ref_batch_generate(st, P(rs.ids), P(rs.labels), B, counter, P(d_ids), P(d_lab), d_ids.numel(),
+                                  P(rs.position_map), P(rs.accessed), N, P(rs.nc), P(rs.ec), len(fanout)) == 0
+    torch.cuda.synchronize()
+    r_nc, r_ids, r_lab = rs.nc.cpu().numpy(), rs.ids.cpu().numpy(), rs.labels.cpu().numpy()
+    assert r_nc[9] == 44
+    buf = rig.dp.alloc_batch(feature_rows=1)
+    orc = oracle.Oracle(indptr, indices, fanout, B)
+    for mode, exact in ((capi.TAIL_REFERENCE, False), (capi.TAIL_EXACT, True)):
+        rig.dp.set_tail_mode(mode)
+        rig.dp.run_once(rig.dp.params(d_ids, d_lab, B, counter, seed=1, batch_id=counter), buf, gather=False)
+        torch.cuda.synchronize()
+        mine = buf.to_host(2)
+        want = orc.run_batch(ids, labels, B, counter, seed=1, batch_id=counter, tail_exact=exact)
+        assert np.array_equal(mine["ids"][:44], want["ids"][:44]) and np.array_equal(mine["labels"], want["labels"][:44])
+        if not exact:  # the reference kernel itself: seeds from 44 * 2 = 88
+            assert np.array_equal(mine["ids"][:44], r_ids[:44]) and np.array_equal(mine["labels"], r_lab[:44])
+            assert np.array_equal(r_ids[:44], ids[88:132])
+        else:
+            assert np.array_equal(mine["ids"][:44], ids[256:300])
+    del tab

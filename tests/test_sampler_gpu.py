@@ -76,8 +76,9 @@ def test_per_op_counter_trace(oracle):
         assert np.array_equal(nc, trace[3 * hop + 1][0]) and np.array_equal(ec, trace[3 * hop + 1][1]), hop
 
 
-def test_edge_cases(oracle):
-    # isolated vertices (deg 0), deg < fanout, duplicate seeds, -1 padded tail, empty batch
+@pytest.mark.parametrize("tail", ["exact", "reference"])
+def test_edge_cases(oracle, tail):
+    # isolated vertices (deg 0), deg < fanout, duplicate seeds, clipped tail (both strides), empty batch
     rng = np.random.default_rng(11)
     N = 400
     deg = rng.integers(0, 9, N)
@@ -91,6 +92,7 @@ def test_edge_cases(oracle):
     ids[5] = ids[3]  # duplicate seed: first position wins in oracle and kernel
     labels = (ids % 3).astype(np.int32)
     rig = Rig(indptr, indices, feat, fanout, B)
+    rig.dp.set_tail_mode(capi.TAIL_REFERENCE if tail == "reference" else capi.TAIL_EXACT)
     d_ids, d_lab = rig.sets(ids, labels)
     buf = rig.dp.alloc_batch()
     orc = oracle.Oracle(indptr, indices, fanout, B)
@@ -99,14 +101,18 @@ def test_edge_cases(oracle):
         p = rig.dp.params(d_ids, d_lab, B, counter, seed=1, batch_id=counter)
         rig.dp.run_once(p, buf)
         torch.cuda.synchronize()
-        want = orc.run_batch(ids, labels, B, counter, seed=1, batch_id=counter)
-        assert_batch_equal(buf.to_host(2), want, 2, feat)
+        want = orc.run_batch(ids, labels, B, counter, seed=1, batch_id=counter, tail_exact=(tail == "exact"))
+        got = buf.to_host(2)
+        assert_batch_equal(got, want, 2, feat)
+        if counter == 3:  # exact: the true tail of the set; reference: clipped size x counter (operator_impl.cu:159-162)
+            first = 120 if tail == "exact" else 30
+            assert np.array_equal(got["ids"][:10], ids[first:first + 10])
     assert want["total_nodes"] == 0 and want["total_edges"] == 0
 
 
-def test_tail_padding_minus_one(oracle):
-    """ids past total_cap become -1 and produce nothing (engine/operator_impl.cu:40-42,218); reached through
-    the kernel-level rule size*counter+idx >= total_cap"""
+@pytest.mark.parametrize("tail", ["exact", "reference"])
+def test_tail_padding_minus_one(oracle, tail):
+    """the clipped tail batch in both stride modes (engine/operator_impl.cu:40-44,159-162)"""
     indptr, indices = small_graph(500, 8.0, 60)
     N = len(indptr) - 1
     ids, labels = make_sets(N, 0.2)  # 100 ids
@@ -114,11 +120,13 @@ def test_tail_padding_minus_one(oracle):
     d_ids, d_lab = rig.sets(ids, labels)
     buf = rig.dp.alloc_batch()
     orc = oracle.Oracle(indptr, indices, [3, 2], 64)
-    p = rig.dp.params(d_ids, d_lab, 64, 1, seed=3, batch_id=1)  # clipped: size = 36, stride 36 (reference quirk)
+    rig.dp.set_tail_mode(capi.TAIL_REFERENCE if tail == "reference" else capi.TAIL_EXACT)
+    p = rig.dp.params(d_ids, d_lab, 64, 1, seed=3, batch_id=1)  # clipped: size = 36; stride 36 (reference quirk) or 64
     rig.dp.run_once(p, buf)
     torch.cuda.synchronize()
-    want = orc.run_batch(ids, labels, 64, 1, seed=3, batch_id=1)
+    want = orc.run_batch(ids, labels, 64, 1, seed=3, batch_id=1, tail_exact=(tail == "exact"))
     assert want["nc"][9] == 36
+    assert np.array_equal(want["ids"][:36], ids[64:100] if tail == "exact" else ids[36:72])
     assert_batch_equal(buf.to_host(2), want, 2)
 
 

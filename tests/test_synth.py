@@ -27,3 +27,19 @@ def test_partition_is_id_mod_parts():
     assert sum(len(p) for p in parts) == 1000
     for p, ids in enumerate(parts):
         assert (ids % 4 == p).all()
+
+
+def test_oracle_host_generator_is_the_numpy_twin(oracle):
+    """oracle/synth_oracle.c (what the CPU arm of bench.py builds its dataset with) == legion_b200/synth.py, bit for bit"""
+    oracle.lib().lgo_set_num_threads(4)
+    for n, dmin, dmax, seed in ((5000, 6.0, 400, 42), (60000, 25.5, 20000, 0x1E910), (1000, 3.3, 50, 7)):
+        ip, ix = synth.graph(n, dmin, dmax, seed)
+        ip2, ix2 = oracle.synth_graph(n, dmin, dmax, seed)
+        assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2)
+    f = synth.features(10, 300, 100, 9)
+    assert np.array_equal(f.view(np.uint32), oracle.synth_features(10, 300, 100, 9).view(np.uint32))
+    ids = np.array([5, -1, 77, 123456], np.int32)
+    r = oracle.synth_feature_rows(ids, 128, 3)
+    assert (r[1] == 0).all()
+    for k in (0, 2, 3):
+        assert np.array_equal(r[k].view(np.uint32), synth.features(int(ids[k]), 1, 128, 3)[0].view(np.uint32))
