@@ -259,6 +259,16 @@ int lg_block_csc(lg_stream_t stream, const int32_t* agg_src, const int32_t* agg_
                  int32_t num_dst, int32_t* indptr, int32_t* indices, int32_t* eids, void* workspace,
                  int64_t workspace_bytes);
 
+/* Every block of a batch in ONE set of launches, sizes read on the device: block h (1..n_hops) = edges [0, ec[9+h]),
+ * destinations [0, nc[9+h-1]) of batch->agg_src / agg_dst (training_backend/ipc_cuda_kernel.cu:218-231).  Nothing is read
+ * on the host, so the call can be enqueued right behind the batch's sampling ops (the server builds the blocks next to
+ * the gather).  max_edges[h-1] / max_dst[h-1] bound block h; indptr / indices / eids are arrays of n_hops device pointers
+ * (eids may be NULL); workspace: lg_block_csc_batch_workspace(n_hops, max_edges) bytes. */
+int lg_block_csc_batch_workspace(int32_t n_hops, const int64_t* max_edges, int64_t* bytes);
+int lg_block_csc_batch(lg_stream_t stream, const lg_batch* batch, int32_t n_hops, const int64_t* max_edges,
+                       const int32_t* max_dst, int32_t* const* indptr, int32_t* const* indices, int32_t* const* eids,
+                       void* workspace, int64_t workspace_bytes);
+
 /* ---- unified cache construction (cache/cache.cu:360-443,71-136,553-611) ---- */
 
 /* aggregate_access (cache/cache_impl.cuh:72-76): agg[i] += part[i]; `part` may be peer memory */
@@ -342,6 +352,9 @@ int lg_vmm_import(int32_t shareable_fd, int64_t bytes, void** ptr);
 int lg_vmm_free(void* ptr);
 int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t bytes); /* cudaHostAllocMapped */
 int lg_host_free(void* host_ptr);
+/* page-lock memory the host already owns (a POSIX shm mapping) so that asynchronous copies into it stay asynchronous */
+int lg_host_register(void* host_ptr, int64_t bytes);
+int lg_host_unregister(void* host_ptr);
 int lg_ipc_export(const void* device_ptr, unsigned char handle[64]);
 int lg_ipc_open(const unsigned char handle[64], void** device_ptr);
 int lg_ipc_close(void* device_ptr);

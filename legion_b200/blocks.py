@@ -39,3 +39,23 @@ class BlockBuilder:
                                        C.c_void_p(eids.data_ptr()) if with_eids else None,
                                        C.c_void_p(self.workspace.data_ptr()), self.workspace.numel()))
         return indptr, indices, eids
+
+    def csc_batch(self, batch_c, hops, max_edges, max_dst):
+        """every block of one batch in one set of launches, sizes read from the batch's counters on the device
+        (lg_block_csc_batch — what the server runs next to the gather).  batch_c: capi.Batch of the batch buffers;
+        max_edges[h-1] / max_dst[h-1] bound block h.  Returns [(indptr, indices, eids) for h = 1..hops], allocated at the
+        bounds: the caller slices them with the counters."""
+        me = (C.c_int64 * hops)(*[int(x) for x in max_edges])
+        md = (C.c_int32 * hops)(*[int(x) for x in max_dst])
+        nb = C.c_int64(0)
+        capi.check(self.L.lg_block_csc_batch_workspace(hops, me, C.byref(nb)))
+        if self.workspace.numel() < nb.value:
+            self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        out = [(torch.empty(int(max_dst[h]) + 1, dtype=torch.int32, device=self.device),
+                torch.empty(int(max_edges[h]), dtype=torch.int32, device=self.device),
+                torch.empty(int(max_edges[h]), dtype=torch.int32, device=self.device)) for h in range(hops)]
+        arr = lambda k: (C.c_void_p * hops)(*[o[k].data_ptr() for o in out])  # noqa: E731
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        capi.check(self.L.lg_block_csc_batch(st, C.byref(batch_c), hops, me, md, arr(0), arr(1), arr(2),
+                                             C.c_void_p(self.workspace.data_ptr()), self.workspace.numel()))
+        return out

@@ -105,6 +105,8 @@ _PROTOS = {
     "lg_vmm_free": (C.c_int, [vp]),
     "lg_host_alloc_mapped": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_int64]),
     "lg_host_free": (C.c_int, [vp]),
+    "lg_host_register": (C.c_int, [vp, C.c_int64]),
+    "lg_host_unregister": (C.c_int, [vp]),
     "lg_ipc_export": (C.c_int, [vp, C.c_char * 64]),
     "lg_ipc_open": (C.c_int, [C.c_char * 64, C.POINTER(vp)]),
     "lg_ipc_close": (C.c_int, [vp]),
@@ -124,6 +126,9 @@ _PROTOS = {
     "lg_device_mem_info": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lg_block_csc_workspace": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),
     "lg_block_csc": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int64]),
+    "lg_block_csc_batch_workspace": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lg_block_csc_batch": (C.c_int, [vp, C.POINTER(Batch), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(vp),
+                                     C.POINTER(vp), C.POINTER(vp), vp, C.c_int64]),
     # include/legion_b200_synth.h
     "lg_synth_indptr": (C.c_int, [vp, C.c_int64, C.c_double, C.c_int32, C.c_uint64, vp]),
     "lg_synth_indices": (C.c_int, [vp, C.c_int64, vp, C.c_uint64, vp]),

@@ -314,6 +314,16 @@ extern "C" int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t 
   if (device_ptr) LG_CUDA(cudaHostGetDevicePointer(device_ptr, *host_ptr, 0));
   return 0;
 }
+extern "C" int lg_host_register(void* host_ptr, int64_t bytes) {
+  LG_REQUIRE(host_ptr && bytes > 0, "lg_host_register: bad argument");
+  LG_CUDA(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable));
+  return 0;
+}
+extern "C" int lg_host_unregister(void* host_ptr) {
+  LG_REQUIRE(host_ptr, "lg_host_unregister: null");
+  LG_CUDA(cudaHostUnregister(host_ptr));
+  return 0;
+}
 extern "C" int lg_host_free(void* host_ptr) {
   {
     std::lock_guard<std::mutex> g(g_huge_mu);

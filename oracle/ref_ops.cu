@@ -8,10 +8,19 @@
 //   cache/cache.cu (+ cache_impl.cuh) : InitPair, InitIndexPair, InitOffsetPair, FeatFillUp, HotnessMeasure,
 //                                       multiGPU_feat_cache_lookup, aggregate_access + bght::bcht maps
 //   engine/memorypool.cu : MemoryPool ctor (needed to link the host wrappers of operator_impl.cu)
+//   cache/cache.cu also carries the HOST code of UnifiedCache::CandidateSelection / CostModel (:360-551), driven below
+//   through the class's own methods; its private state (hotness arrays, capacities) is reached by compiling the
+//   reference headers with `private` spelled `public` — test infrastructure, nothing of this ships.
+#include <algorithm>
+#include <cstdint>
+#include <iostream>
+#include <vector>
+#define private public
 #include "engine/memorypool.cu"
 #include "cache/cache.cu"
 #undef cudaCheckError
 #include "engine/operator_impl.cu"
+#undef private
 
 #include <cstdint>
 
@@ -130,6 +139,88 @@ int ref_bcht_build_and_find(cudaStream_t st, int32_t* pair_kv, int32_t n_pairs, 
   delete map;
   REF_OK();
   return ok ? 0 : -1;
+}
+
+// ---- UnifiedCache::CandidateSelection + CostModel (cache/cache.cu:360-551) on one device ----
+namespace {
+struct StubFeature : public FeatureStorage {
+  int32_t n, dim;
+  void Build(BuildInfo*, int) override {}
+  void Finalize() override {}
+  int32_t* GetTrainingSetIds(int32_t) const override { return nullptr; }
+  int32_t* GetValidationSetIds(int32_t) const override { return nullptr; }
+  int32_t* GetTestingSetIds(int32_t) const override { return nullptr; }
+  int32_t* GetTrainingLabels(int32_t) const override { return nullptr; }
+  int32_t* GetValidationLabels(int32_t) const override { return nullptr; }
+  int32_t* GetTestingLabels(int32_t) const override { return nullptr; }
+  int32_t TrainingSetSize(int32_t) const override { return 0; }
+  int32_t ValidationSetSize(int32_t) const override { return 0; }
+  int32_t TestingSetSize(int32_t) const override { return 0; }
+  int32_t TotalNodeNum() const override { return n; }
+  float* GetAllFloatFeature() const override { return nullptr; }
+  int32_t GetFloatFeatureLen() const override { return dim; }
+  void IOSubmit(int32_t*, int32_t*, int32_t*, float*, int32_t, int32_t, cudaStream_t) override {}
+  void IOComplete() override {}
+};
+struct StubGraph : public GraphStorage {
+  int64_t* indptr;  // device-readable (GetEdgeMem dereferences it in a kernel, cache/cache_impl.cuh:63-69)
+  void Build(BuildInfo*) override {}
+  void GraphCache(int32_t*, int32_t, int32_t, int32_t) override {}
+  void Finalize() override {}
+  int32_t GetPartitionCount() const override { return 1; }
+  int64_t** GetCSRNodeIndex(int32_t) const override { return nullptr; }
+  int32_t** GetCSRNodeMatrix(int32_t) const override { return nullptr; }
+  int64_t* GetCSRNodeIndexCPU() const override { return indptr; }
+  int32_t* GetCSRNodeMatrixCPU() const override { return nullptr; }
+  int64_t Src_Size(int32_t) const override { return 0; }
+  int64_t Dst_Size(int32_t) const override { return 0; }
+  char* PartitionIndex(int32_t) const override { return nullptr; }
+  int32_t* PartitionOffset(int32_t) const override { return nullptr; }
+};
+}  // namespace
+
+// Kg controllers, all on the current device; node_hot/edge_hot: Kg host arrays of N counters each; max_ids: Kg values.
+// Outputs: per-GPU capacities exactly as UnifiedCache stores them (node_capacity_[0], edge_capacity_[0]); optionally the
+// reference's own ranking (QF/QT, int32[N]) and sorted aggregates (AF/AT, u64[N]) copied to the host.
+int ref_cost_model(int32_t N, int32_t dim, int64_t cache_memory, int32_t Kg, int32_t train_step,
+                   const unsigned long long* const* node_hot, const unsigned long long* const* edge_hot,
+                   const int32_t* max_ids, const int64_t* indptr_host, uint64_t topo_counter0, uint64_t topo_counter1,
+                   int32_t* node_capacity, int32_t* edge_capacity, int32_t* QF, int32_t* QT, unsigned long long* AF,
+                   unsigned long long* AT) {
+  int mode = 0;
+  while ((1 << mode) < Kg) mode++;
+  if ((1 << mode) != Kg || mode > 3) return -2;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  UnifiedCache uc;
+  uc.Initialize(cache_memory, dim, train_step, Kg, 0, 0);
+  const size_t nb = (size_t)N * sizeof(unsigned long long);
+  for (int j = 0; j < Kg; j++) {
+    uc.cache_controller_[j]->Initialize(dev, N);  // every controller on this device (the box may have one GPU)
+    cudaMemcpy(uc.cache_controller_[j]->GetNodeAccessedMap(), node_hot[j], nb, cudaMemcpyHostToDevice);
+    cudaMemcpy(uc.cache_controller_[j]->GetEdgeAccessedMap(), edge_hot[j], nb, cudaMemcpyHostToDevice);
+    static_cast<PreSCCacheController*>(uc.cache_controller_[j])->max_ids_ = max_ids[j];
+  }
+  StubFeature feat;
+  feat.n = N;
+  feat.dim = dim;
+  StubGraph graph;
+  cudaMallocManaged(&graph.indptr, (size_t)(N + 1) * sizeof(int64_t));
+  memcpy(graph.indptr, indptr_host, (size_t)(N + 1) * sizeof(int64_t));
+  uc.CandidateSelection(mode, &feat, &graph);
+  if (uc.Kg_ != Kg || uc.Kc_ != 1) return -3;
+  std::vector<uint64_t> counters = {topo_counter0, topo_counter1};
+  uc.CostModel(mode, &feat, &graph, counters, train_step);
+  cudaDeviceSynchronize();
+  *node_capacity = uc.node_capacity_[0];
+  *edge_capacity = uc.edge_capacity_[0];
+  if (QF) cudaMemcpy(QF, uc.QF_[0], (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (QT) cudaMemcpy(QT, uc.QT_[0], (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (AF) cudaMemcpy(AF, uc.AF_[0], nb, cudaMemcpyDeviceToHost);
+  if (AT) cudaMemcpy(AT, uc.AT_[0], nb, cudaMemcpyDeviceToHost);
+  cudaFree(graph.indptr);
+  REF_OK();
+  return 0;
 }
 
 }  // extern "C"

@@ -46,6 +46,12 @@ int32_t UnifiedCache::MaxIdNum(int32_t dev) {
   return v;
 }
 
+void UnifiedCache::ReadTierRows(int32_t dev, unsigned long long out[3]) {
+  LGCHECK(lg_set_device(dev));
+  LGCHECK(lg_memcpy_d2h(out, tier_rows_[dev], 3 * 8, nullptr));
+  LGCHECK(lg_stream_synchronize(nullptr));
+}
+
 void UnifiedCache::CandidateSelection(int cache_agg_mode, FeatureStorage* feature, GraphStorage*) {
   Kg_ = 1 << cache_agg_mode;  // cache.cu:375-389
   if (Kg_ > device_count_) Kg_ = device_count_;

@@ -23,6 +23,7 @@ class UnifiedCache {
   int32_t NodeCapacity(int clique) const { return node_capacity_[clique]; }
   int32_t EdgeCapacity(int clique) const { return edge_capacity_[clique]; }
   unsigned long long* TierRows(int32_t dev) { return tier_rows_[dev]; }
+  void ReadTierRows(int32_t dev, unsigned long long out[3]);  // synchronous copy of the device counters
 
  private:
   int64_t cache_memory_ = 0;

@@ -5,6 +5,8 @@
 // so cudaIpcGetMemHandle works with the trainer's legacy cudaIpcOpenMemHandle).
 #include "ipc_service.h"
 
+#include "../../include/legion_b200_ext.h"
+
 #include <fcntl.h>
 #include <semaphore.h>
 #include <sys/mman.h>
@@ -45,6 +47,27 @@ class CUDAIPCEnv : public IPCEnv {
     feature_rows_.assign(device_count, 0);
     semr_.resize(device_count);
     semw_.resize(device_count);
+    OpenExt();
+  }
+
+  // the optional side channel (include/legion_b200_ext.h); LEGION_EXT_SHM=0 = the reference wire and nothing else
+  void OpenExt() {
+    const char* e = std::getenv("LEGION_EXT_SHM");
+    if (e && std::atoi(e) == 0) return;
+    shm_unlink(LG_EXT_SHM_NAME);  // never inherit a crashed run's sequence numbers
+    ext_fd_ = shm_open(LG_EXT_SHM_NAME, O_RDWR | O_CREAT, 0777);
+    if (ext_fd_ < 0 || ftruncate(ext_fd_, sizeof(lg_ext_shm)) != 0) return;
+    void* addr = mmap(0, sizeof(lg_ext_shm), PROT_READ | PROT_WRITE, MAP_SHARED, ext_fd_, 0);
+    if (addr == MAP_FAILED) return;
+    std::memset(addr, 0, sizeof(lg_ext_shm));
+    if (lg_host_register(addr, sizeof(lg_ext_shm)) != 0) {  // pageable would make the copies synchronous: do without
+      munmap(addr, sizeof(lg_ext_shm));
+      return;
+    }
+    ext_ = (lg_ext_shm*)addr;
+    ext_->n_gpus = device_count_;
+    ext_->version = LG_EXT_VERSION;
+    ext_->magic = LG_EXT_MAGIC;
   }
 
   void Coordinate(BuildInfo* info) override {
@@ -146,7 +169,43 @@ class CUDAIPCEnv : public IPCEnv {
   int32_t* GetEdgeCounter(int32_t d, int32_t p) override { return (int32_t*)edge_counter_[d][p % pipeline_depth_]; }
   int64_t GetFeatureRows(int32_t d) override { return feature_rows_[d]; }
 
-  void IPCPost(int32_t d, int32_t p) override { sem_post(semw_[d][p]); }
+  int32_t* GetHostCounters(int32_t d, int32_t p) override {
+    return (ext_ && d < LG_EXT_MAX_DEVICE && p < LG_EXT_SLOTS) ? (int32_t*)ext_->counters[d][p] : nullptr;
+  }
+
+  bool InitializeCscBuffers(int32_t dev, int32_t depth, int32_t hops, const int64_t* max_edges, const int64_t* max_dst) override {
+    const char* e = std::getenv("LEGION_EMIT_CSC");
+    if (!ext_ || !e || std::atoi(e) == 0 || hops > LG_EXT_MAX_HOPS || dev >= LG_EXT_MAX_DEVICE || depth > LG_EXT_SLOTS) return false;
+    LGCHECK(lg_set_device(dev));
+    if ((int32_t)csc_.size() < device_count_) csc_.resize(device_count_);
+    csc_[dev].assign((size_t)depth * hops * 3, nullptr);
+    for (int32_t p = 0; p < depth; p++)
+      for (int32_t h = 0; h < hops; h++)
+        for (int32_t k = 0; k < 3; k++) {
+          const int64_t words = k == 0 ? max_dst[h] + 1 : max_edges[h];
+          void* ptr = nullptr;
+          LGCHECK(lg_device_alloc(&ptr, words * 4));
+          LGCHECK(lg_memset_async(ptr, 0, words * 4, nullptr));
+          LGCHECK(lg_ipc_export(ptr, ext_->csc_handle[dev][p][h][k]));
+          csc_[dev][((size_t)p * hops + h) * 3 + k] = ptr;
+        }
+    LGCHECK(lg_stream_synchronize(nullptr));
+    csc_hops_ = hops;
+    ext_->csc_hops = hops;
+    return true;
+  }
+  int32_t* GetCsc(int32_t dev, int32_t p, int32_t hop, int32_t which) override {
+    if (csc_hops_ == 0 || dev >= (int32_t)csc_.size() || csc_[dev].empty()) return nullptr;
+    return (int32_t*)csc_[dev][((size_t)(p % pipeline_depth_) * csc_hops_ + (hop - 1)) * 3 + which];
+  }
+
+  void IPCPost(int32_t d, int32_t p) override {
+    if (ext_ && d < LG_EXT_MAX_DEVICE && p < LG_EXT_SLOTS) {
+      ext_->seq[d][p] = ext_->seq[d][p] + 1;  // the counters of this batch are in place (the runner joined its streams)
+      __sync_synchronize();
+    }
+    sem_post(semw_[d][p]);
+  }
   void IPCWait(int32_t d, int32_t p) override { sem_wait(semr_[d][p]); }
 
   void Finalize() override {
@@ -166,9 +225,21 @@ class CUDAIPCEnv : public IPCEnv {
         sem_unlink(("sem_w_" + std::to_string(i) + "_" + std::to_string(j)).c_str());
       }
     }
+    for (size_t i = 0; i < csc_.size(); i++) {
+      if (csc_[i].empty()) continue;
+      LGCHECK(lg_set_device((int32_t)i));
+      for (void* ptr : csc_[i]) lg_device_free(ptr);
+    }
     munmap((void*)shm_, sizeof(shmStruct));
     close(fd_);
     shm_unlink(kShmName);
+    if (ext_) {
+      lg_host_unregister((void*)ext_);
+      munmap((void*)ext_, sizeof(lg_ext_shm));
+      close(ext_fd_);
+      shm_unlink(LG_EXT_SHM_NAME);
+      ext_ = nullptr;
+    }
   }
 
   int32_t GetTrainStep() override { return train_step_; }
@@ -176,6 +247,10 @@ class CUDAIPCEnv : public IPCEnv {
  private:
   volatile shmStruct* shm_ = nullptr;
   int fd_ = -1;
+  lg_ext_shm* ext_ = nullptr;
+  int ext_fd_ = -1;
+  std::vector<std::vector<void*>> csc_;  // [gpu][(slot * hops + h) * 3 + k]
+  int32_t csc_hops_ = 0;
   std::vector<std::vector<void*>> ids_, float_features_, labels_, agg_src_, agg_dst_, node_counter_, edge_counter_;
   std::vector<int64_t> feature_rows_;
   std::vector<std::vector<sem_t*>> semr_, semw_;

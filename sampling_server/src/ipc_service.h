@@ -37,6 +37,14 @@ class IPCEnv {
   virtual int32_t* GetNodeCounter(int32_t dev_id, int32_t current_pipe) = 0;
   virtual int32_t* GetEdgeCounter(int32_t dev_id, int32_t current_pipe) = 0;
   virtual int64_t GetFeatureRows(int32_t dev_id) = 0;
+  // host words (node_counter[16] | edge_counter[16]) of the side channel include/legion_b200_ext.h, or nullptr when it
+  // is disabled: the runner copies the batch's counters there behind its last kernel, IPCPost publishes them
+  virtual int32_t* GetHostCounters(int32_t dev_id, int32_t current_pipe) = 0;
+  // LEGION_EMIT_CSC=1 and the side channel is up: three more CUDA-IPC buffers per (gpu, slot, block) for the blocks as
+  // CSC (include/legion_b200_ext.h).  max_edges[h-1] / max_dst[h-1] bound block h.  Returns false when disabled.
+  virtual bool InitializeCscBuffers(int32_t dev_id, int32_t pipeline_depth, int32_t hops, const int64_t* max_edges,
+                                    const int64_t* max_dst) = 0;
+  virtual int32_t* GetCsc(int32_t dev_id, int32_t current_pipe, int32_t hop, int32_t which) = 0;  // which: 0 indptr, 1 indices, 2 eids
   virtual void IPCPost(int32_t dev_id, int32_t current_pipe) = 0;
   virtual void IPCWait(int32_t dev_id, int32_t current_pipe) = 0;
   virtual void Finalize() = 0;

@@ -19,7 +19,11 @@ class MemoryPool {
   int32_t GetGlobalBatchId() const { return global_batch_id_; }
   lg_batch* Batch() { return &batch_[current_pipe_]; }
   lg_batch* Batch(int pipe) { return &batch_[pipe]; }
-  lg_sampler* sampler = nullptr;
+  // one sampler handle (position map, scan state, frontier scratch) per pipeline slot: the sampling of batch i+1
+  // does not queue behind batch i's on a shared handle (the reference has one scratch set per GPU, engine/server.cu:221-234)
+  lg_sampler* Sampler() { return samplers[samplers.size() > 1 ? current_pipe_ : 0]; }
+  lg_sampler* Sampler(int pipe) { return samplers[samplers.size() > 1 ? pipe : 0]; }
+  std::vector<lg_sampler*> samplers;
   int32_t rng_kind = LG_RNG_PHILOX;
   uint64_t rng_seed = 0x1E910;
 

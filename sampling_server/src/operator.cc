@@ -29,7 +29,7 @@ class BatchGenerateOP : public Operator {
     } else {
       ids = feature->GetTestingSetIds(dev); labels = feature->GetTestingLabels(dev); cap = feature->TestingSetSize(dev);
     }
-    LGCHECK(lg_batch_generate(pool->sampler, params->stream, ids, labels, cap, batch_size, iter, pool->Batch()));
+    LGCHECK(lg_batch_generate(pool->Sampler(), params->stream, ids, labels, cap, batch_size, iter, pool->Batch()));
     LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:
@@ -46,7 +46,7 @@ class RandomSampleOP : public Operator {
     int32_t dev = params->device_id;
     // presampling reads the host CSR directly and counts edge accesses (pre_sample, operator_impl.cu:301-397)
     unsigned long long* edge_hot = params->is_presc ? cache->GetEdgeAccessedMap(dev) : nullptr;
-    LGCHECK(lg_random_sample(pool->sampler, params->stream, graph->Topology(dev), op_id_ / INTRABATCH_CON, pool->rng_kind,
+    LGCHECK(lg_random_sample(pool->Sampler(), params->stream, graph->Topology(dev), op_id_ / INTRABATCH_CON, pool->rng_kind,
                              pool->rng_seed, (uint32_t)pool->GetGlobalBatchId(), (uint32_t)dev, pool->Batch(), edge_hot));
     LGCHECK(lg_event_record(params->event, params->stream));
   }
@@ -71,10 +71,10 @@ class CacheLookupOP : public Operator {
     int32_t dev = params->device_id;
     const bool last = op_id_ / INTRABATCH_CON == params->hop_num;
     if (!fuse)
-      LGCHECK(lg_feature_cache_lookup(pool->sampler, params->stream, cache->FeatureCache(dev), op_id_, cache->LocalPart(dev),
+      LGCHECK(lg_feature_cache_lookup(pool->Sampler(), params->stream, cache->FeatureCache(dev), op_id_, cache->LocalPart(dev),
                                       pool->Batch(), cache->TierRows(dev)));
     else if (last)
-      LGCHECK(lg_feature_cache_lookup_range(pool->sampler, params->stream, cache->FeatureCache(dev), op_id_, 0,
+      LGCHECK(lg_feature_cache_lookup_range(pool->Sampler(), params->stream, cache->FeatureCache(dev), op_id_, 0,
                                             cache->LocalPart(dev), pool->Batch(), cache->TierRows(dev)));
     LGCHECK(lg_event_record(params->event, params->stream));
   }
@@ -87,7 +87,7 @@ class SSDIOSubmitOP : public Operator {
   explicit SSDIOSubmitOP(int op_id) : op_id_(op_id) {}
   void run(OpParams* params) override {
     auto* pool = (MemoryPool*)params->memorypool;
-    LGCHECK(lg_io_submit(pool->sampler, params->stream, op_id_, pool->Batch()));
+    LGCHECK(lg_io_submit(pool->Sampler(), params->stream, op_id_, pool->Batch()));
     LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:
@@ -102,7 +102,7 @@ class SSDIOCompleteOP : public Operator {
     auto* cache = (UnifiedCache*)params->cache;
     int32_t dev = params->device_id;
     bool presc = params->is_presc;
-    LGCHECK(lg_io_complete(pool->sampler, params->stream, pool->GetCurrentMode(), pool->Batch(),
+    LGCHECK(lg_io_complete(pool->Sampler(), params->stream, pool->GetCurrentMode(), pool->Batch(),
                            presc ? cache->GetNodeAccessedMap(dev) : nullptr, presc ? cache->MaxIdsDevice(dev) : nullptr));
     LGCHECK(lg_event_record(params->event, params->stream));
   }

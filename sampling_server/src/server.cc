@@ -6,6 +6,8 @@
 #include "server.h"
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <thread>
@@ -79,13 +81,38 @@ class GPUServer : public Server {
   }
 
   void Run() override {
+    auto t1 = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
     for (int i = 0; i < shard_count_; i++) pool.emplace_back(&RunnerLoop, max_step_, runners_[i], params_[i]);
     for (auto& th : pool) th.join();
+    serve_seconds_ = std::chrono::duration_cast<std::chrono::duration<double>>(std::chrono::steady_clock::now() - t1).count();
+  }
+
+  // One JSON line per GPU: rows gathered per tier over the whole run (local HBM shard / peer shard over NVLink / host
+  // backing matrix over PCIe), and the bytes those rows moved per second of serving (metrics row: the
+  // reference only has commented-out hit-rate printing, cache/cache.cu:197-214).
+  void Telemetry() {
+    const int dim = feature_->GetFloatFeatureLen();
+    for (int i = 0; i < shard_count_; i++) {
+      unsigned long long rows[3] = {0, 0, 0};
+      cache_->ReadTierRows(i, rows);
+      const double tot = (double)(rows[0] + rows[1] + rows[2]), s = serve_seconds_ > 0 ? serve_seconds_ : 1.0;
+      std::printf("{\"legion_b200_telemetry\": {\"gpu\": %d, \"batches\": %d, \"serve_seconds\": %.4f, \"rows\": {\"local\": %llu, "
+                  "\"peer\": %llu, \"host\": %llu}, \"hit_mix\": {\"local\": %.4f, \"peer\": %.4f, \"host\": %.4f}, "
+                  "\"GBps\": {\"local_hbm\": %.2f, \"peer_nvlink\": %.2f, \"host_pcie\": %.2f}, \"seeds_per_s\": %.1f}}\n",
+                  i, max_step_, serve_seconds_, rows[0], rows[1], rows[2], tot > 0 ? rows[0] / tot : 0.0,
+                  tot > 0 ? rows[1] / tot : 0.0, tot > 0 ? rows[2] / tot : 0.0, rows[0] * 4.0 * dim / s / 1e9,
+                  rows[1] * 4.0 * dim / s / 1e9, rows[2] * 4.0 * dim / s / 1e9, (double)seeds_served_[i] / s);
+    }
+    std::fflush(stdout);
   }
 
   void Finalize() override {
     for (int i = 0; i < shard_count_; i++) runners_[i]->Finalize(params_[i]);
+    seeds_served_.assign(shard_count_, 0);
+    for (int i = 0; i < shard_count_; i++)
+      for (int g = 0; g < max_step_; g++) seeds_served_[i] += ipc_env_->GetCurrentBatchsize(i, ipc_env_->GetCurrentMode(g));
+    Telemetry();
     graph_->Finalize();
     feature_->Finalize();
     ipc_env_->Finalize();
@@ -99,6 +126,8 @@ class GPUServer : public Server {
   UnifiedCache* cache_ = nullptr;
   IPCEnv* ipc_env_ = nullptr;
   int shard_count_ = 0, train_step_ = 0, max_step_ = 0;
+  double serve_seconds_ = 0.0;
+  std::vector<long long> seeds_served_;
   std::vector<Runner*> runners_;
   std::vector<RunnerParams*> params_;
 };
@@ -111,8 +140,18 @@ class GPURunner : public Runner {
     auto* cache = (UnifiedCache*)params->cache;
     auto* feature = (FeatureStorage*)params->feature;
     auto* env = (IPCEnv*)params->env;
-    streams_.resize(INTRABATCH_CON);
-    for (auto& s : streams_) LGCHECK(lg_stream_create(&s));
+    interbatch_concurrency_ = INTERBATCH_CON;
+    {  // LEGION_SLOT_SAMPLERS=0: one sampler handle and one stream triple per GPU, as in the reference
+      const char* e = std::getenv("LEGION_SLOT_SAMPLERS");
+      slot_samplers_ = !(e && std::atoi(e) == 0);
+    }
+    // three streams per pipeline slot (the reference has three per GPU, engine/server.cu:181-184): with a sampler handle per
+    // slot the chains of consecutive batches are independent, so they must not share stream 0 either
+    streams_.resize(slot_samplers_ ? interbatch_concurrency_ : 1);
+    for (auto& ss : streams_) {
+      ss.resize(INTRABATCH_CON);
+      for (auto& s : ss) LGCHECK(lg_stream_create(&s));
+    }
     int batch_size = env->GetRawBatchsize();
     int hop_num = (int)params->fanout.size();
     num_ids_ = (int32_t)lg_num_ids(batch_size, params->fanout.data(), hop_num);  // server.cu:187-199
@@ -127,26 +166,59 @@ class GPURunner : public Runner {
       ops_[INTRABATCH_CON * i + 5] = NewSSDIOSubmitOP(INTRABATCH_CON * i + 5);
     }
     ops_[op_num_ - 1] = NewSSDIOCompleteOP(op_num_ - 1);
-    interbatch_concurrency_ = INTERBATCH_CON;
     cache->InitializeCacheController(local_dev_id_, feature->TotalNodeNum());
     memorypool_ = new MemoryPool(interbatch_concurrency_);
     // valid/test batches can be larger than the raw batch only if their sets are (512-sized steps): take the max
     int max_batch = batch_size;
     for (int m : {VALIDMODE, TESTMODE})
       if (env->GetCurrentBatchsize(local_dev_id_, m) > max_batch) max_batch = env->GetCurrentBatchsize(local_dev_id_, m);
-    LGCHECK(lg_sampler_create(local_dev_id_, max_batch, params->fanout.data(), hop_num, feature->TotalNodeNum(), &memorypool_->sampler));
+    memorypool_->samplers.assign(slot_samplers_ ? interbatch_concurrency_ : 1, nullptr);
     if (max_batch > batch_size) num_ids_ = (int32_t)lg_num_ids(max_batch, params->fanout.data(), hop_num);
     if (const char* e = std::getenv("LEGION_RNG")) memorypool_->rng_kind = std::strcmp(e, "minstd") == 0 ? LG_RNG_MINSTD : LG_RNG_PHILOX;
     if (const char* e = std::getenv("LEGION_SEED")) memorypool_->rng_seed = std::strtoull(e, nullptr, 0);
-    if (const char* e = std::getenv("LEGION_GATHER")) LGCHECK(lg_sampler_set_gather_variant(memorypool_->sampler, std::atoi(e)));
-    {  // the trainer only sees a batch after its last op: let hop h+1 finish hop h's construct_graph and the last
-       // sampling op release the position map (two launches less per batch); LEGION_LAZY_RELABEL=0 = every op complete
+    for (auto& smp : memorypool_->samplers) {
+      LGCHECK(lg_sampler_create(local_dev_id_, max_batch, params->fanout.data(), hop_num, feature->TotalNodeNum(), &smp));
+      if (const char* e = std::getenv("LEGION_GATHER")) LGCHECK(lg_sampler_set_gather_variant(smp, std::atoi(e)));
+      if (const char* e = std::getenv("LEGION_TAIL"))  // "reference": the clipped tail batch strides like the reference's
+        LGCHECK(lg_sampler_set_tail_mode(smp, std::strcmp(e, "reference") == 0 ? LG_TAIL_REFERENCE : LG_TAIL_EXACT));
+      // the trainer only sees a batch after its last op: let hop h+1 finish hop h's construct_graph and the last
+      // sampling op release the position map (two launches less per batch); LEGION_LAZY_RELABEL=0 = every op complete
       const char* e = std::getenv("LEGION_LAZY_RELABEL");
-      LGCHECK(lg_sampler_set_lazy_relabel(memorypool_->sampler, (e && std::atoi(e) == 0) ? 0 : 1));
+      LGCHECK(lg_sampler_set_lazy_relabel(smp, (e && std::atoi(e) == 0) ? 0 : 1));
     }
     float_feature_len_ = feature->GetFloatFeatureLen();
     max_batch_ = max_batch;
     env->InitializeSamplesBuffer(max_batch, num_ids_, float_feature_len_, local_dev_id_, interbatch_concurrency_);
+    {  // blocks as CSC, built by the server on the third stream next to the gather (LEGION_EMIT_CSC=1): bounds per block
+      csc_max_edges_.assign(hop_num, 0);
+      csc_max_dst_.assign(hop_num, 0);
+      int64_t per = max_batch, nodes = max_batch, edges = 0;
+      for (int h = 0; h < hop_num; h++) {
+        csc_max_dst_[h] = nodes;  // destinations of block h+1 = every vertex of hops 0..h
+        per *= params->fanout[h];
+        edges += per;
+        nodes += per;
+        csc_max_edges_[h] = edges;  // cumulative edges of hops 1..h+1
+      }
+      emit_csc_ = env->InitializeCscBuffers(local_dev_id_, interbatch_concurrency_, hop_num, csc_max_edges_.data(), csc_max_dst_.data());
+      if (emit_csc_) {
+        int64_t nb = 0;
+        LGCHECK(lg_block_csc_batch_workspace(hop_num, csc_max_edges_.data(), &nb));
+        csc_max_dst32_.assign(csc_max_dst_.begin(), csc_max_dst_.end());
+        csc_ptrs_.assign((size_t)interbatch_concurrency_ * 3 * hop_num, nullptr);
+        for (int p = 0; p < interbatch_concurrency_; p++)
+          for (int k = 0; k < 3; k++)
+            for (int h = 1; h <= hop_num; h++) csc_ptrs_[((size_t)p * 3 + k) * hop_num + (h - 1)] = env->GetCsc(local_dev_id_, p, h, k);
+        csc_workspace_bytes_ = nb;
+        csc_workspace_.assign(interbatch_concurrency_, nullptr);
+        csc_ev_.resize(interbatch_concurrency_);
+        for (int i = 0; i < interbatch_concurrency_; i++) {
+          LGCHECK(lg_device_alloc(&csc_workspace_[i], nb));
+          LGCHECK(lg_event_create(&csc_ev_[i]));
+        }
+        if (local_dev_id_ == 0) std::cout << "Blocks are emitted as CSC (LEGION_EMIT_CSC)\n";
+      }
+    }
     current_pipe_ = 0;
     for (int i = 0; i < interbatch_concurrency_; i++) {
       lg_batch* b = memorypool_->Batch(i);
@@ -178,7 +250,7 @@ class GPURunner : public Runner {
     for (int i = 0; i < op_num_; i++) {
       auto* op = new OpParams();
       op->device_id = local_dev_id_;
-      op->stream = streams_[i % INTRABATCH_CON];
+      op->stream = streams_[0][i % INTRABATCH_CON];
       op->event = events_[0][i];
       op->memorypool = memorypool_;
       op->cache = cache;
@@ -218,6 +290,7 @@ class GPURunner : public Runner {
     memorypool_->SetCurrentPipe(0);
     for (int i = 0; i < op_num_; i += INTRABATCH_CON) {  // ops 0,3,6,..: all on stream 0
       op_params_[i]->is_presc = true;
+      op_params_[i]->stream = streams_[0][i % INTRABATCH_CON];
       op_params_[i]->event = events_[0][i];
       ops_[i]->run(op_params_[i]);
     }
@@ -238,17 +311,35 @@ class GPURunner : public Runner {
     memorypool_->SetCurrentPipe(current_pipe_);
     env->IPCWait(local_dev_id_, current_pipe_);
     auto& ev = events_[current_pipe_];
+    auto& st = streams_[slot_samplers_ ? current_pipe_ : 0];
     for (int i = 0; i < op_num_; i++) {
       if (i % INTRABATCH_CON >= 1)  // lookup / io ops wait for the sampling op of their hop (server.cu:312-314)
-        LGCHECK(lg_stream_wait_event(streams_[i % INTRABATCH_CON], ev[i / INTRABATCH_CON * INTRABATCH_CON]));
+        LGCHECK(lg_stream_wait_event(st[i % INTRABATCH_CON], ev[i / INTRABATCH_CON * INTRABATCH_CON]));
       op_params_[i]->is_presc = false;
+      op_params_[i]->stream = st[i % INTRABATCH_CON];
       op_params_[i]->event = ev[i];
       ops_[i]->run(op_params_[i]);
     }
+    if (emit_csc_) {  // the third stream is idle in the reference (SSDIOSubmit is a no-op): the blocks are built there, behind
+                      // the last sampling op, while the gather streams on the second
+      LGCHECK(lg_stream_wait_event(st[2], ev[op_num_ - 1 - INTRABATCH_CON]));
+      const int hops = (int)csc_max_edges_.size();
+      int32_t** ptrs = &csc_ptrs_[(size_t)current_pipe_ * 3 * hops];  // [indptr | indices | eids][block]
+      LGCHECK(lg_block_csc_batch(st[2], memorypool_->Batch(current_pipe_), hops, csc_max_edges_.data(), csc_max_dst32_.data(),
+                                 ptrs, ptrs + hops, ptrs + 2 * hops, csc_workspace_[current_pipe_], csc_workspace_bytes_));
+      LGCHECK(lg_event_record(csc_ev_[current_pipe_], st[2]));
+    }
+    // the side channel (include/legion_b200_ext.h): the batch's counters go to host memory behind its last lookup (which
+    // waited for the last sampling op), so that the trainer's get_next needs no device copy of its own
+    if (int32_t* hc = env->GetHostCounters(local_dev_id_, current_pipe_)) {
+      const lg_batch* b = memorypool_->Batch(current_pipe_);
+      LGCHECK(lg_memcpy_d2h(hc, b->node_counter, LG_COUNTER_SLOTS * sizeof(int32_t), st[1]));
+      LGCHECK(lg_memcpy_d2h(hc + LG_COUNTER_SLOTS, b->edge_counter, LG_COUNTER_SLOTS * sizeof(int32_t), st[1]));
+    }
     // the sticky overflow flag as of this batch's last lookup: an asynchronous copy behind it (a synchronous read on any
     // of the three streams would wait for the batch just launched, not for the one being handed off)
-    LGCHECK(lg_sampler_status_async(memorypool_->sampler, streams_[1], status_host_[current_pipe_]));
-    LGCHECK(lg_event_record(status_ev_[current_pipe_], streams_[1]));
+    LGCHECK(lg_sampler_status_async(memorypool_->Sampler(), st[1], status_host_[current_pipe_]));
+    LGCHECK(lg_event_record(status_ev_[current_pipe_], st[1]));
     if (pending_pipe_ >= 0) Complete(env, pending_pipe_, pending_batch_);
     pending_pipe_ = current_pipe_;
     pending_batch_ = batch_id;
@@ -264,6 +355,7 @@ class GPURunner : public Runner {
     for (int i = op_num_ - INTRABATCH_CON; i < op_num_; i++)  // join all three streams before the hand-off
       LGCHECK(lg_event_synchronize(ev[i]));
     LGCHECK(lg_event_synchronize(status_ev_[pipe]));
+    if (emit_csc_) LGCHECK(lg_event_synchronize(csc_ev_[pipe]));
     const int32_t st = *status_host_[pipe];
     if (st != 0) {
       std::fprintf(stderr, "batch %d on GPU %d overflowed its buffers (status %d)\n", batch_id, local_dev_id_, st);
@@ -280,19 +372,28 @@ class GPURunner : public Runner {
     pending_pipe_ = -1;
     env->IPCWait(local_dev_id_, (current_pipe_ + 1) % interbatch_concurrency_);  // server.cu:336
     LGCHECK(lg_set_device(local_dev_id_));
-    lg_sampler_destroy(memorypool_->sampler);
+    for (auto* smp : memorypool_->samplers) lg_sampler_destroy(smp);
     for (auto& ev : events_)
       for (auto& e : ev) lg_event_destroy(e);
     for (auto& e : status_ev_) lg_event_destroy(e);
     for (auto* h : status_host_) lg_host_free(h);
-    for (auto& s : streams_) lg_stream_destroy(s);
+    for (auto& ss : streams_)
+      for (auto& s : ss) lg_stream_destroy(s);
   }
 
  private:
   int32_t num_ids_ = 0, float_feature_len_ = 0, max_batch_ = 0;
   MemoryPool* memorypool_ = nullptr;
   int current_pipe_ = 0, interbatch_concurrency_ = INTERBATCH_CON, local_dev_id_ = 0, mode_ = 0, op_num_ = 0;
-  std::vector<lg_stream_t> streams_;
+  bool slot_samplers_ = true;
+  bool emit_csc_ = false;
+  std::vector<int64_t> csc_max_edges_, csc_max_dst_;
+  std::vector<int32_t> csc_max_dst32_;
+  std::vector<int32_t*> csc_ptrs_;  // [slot][indptr | indices | eids][block]
+  std::vector<void*> csc_workspace_;
+  int64_t csc_workspace_bytes_ = 0;
+  std::vector<lg_event_t> csc_ev_;
+  std::vector<std::vector<lg_stream_t>> streams_;  // [slot][INTRABATCH_CON]
   std::vector<std::vector<lg_event_t>> events_;  // [slot][op]
   int pending_pipe_ = -1;
   int32_t pending_batch_ = 0;

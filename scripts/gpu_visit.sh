@@ -4,7 +4,7 @@
 tag=$1; shift
 mkdir -p gpurun_out
 if [ "$1" = "pytest" ]; then
-  python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
+  python -m pytest tests -m gpu -x -q -rs > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
   tail -5 gpurun_out/${tag}_pytest.log
 fi
 while read -r name args; do

@@ -19,7 +19,8 @@ ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--epochs", type=int, default=10)
 ap.add_argument("--cache-gb", type=float, default=100.0)
 ap.add_argument("--dir", default="/dev/shm/legion_ds")
-ap.add_argument("--csc", action="store_true", help="consumer also builds the CSC of every block (lg_block_csc)")
+ap.add_argument("--csc", action="store_true", help="consume through get_next_csc: the CSC of every block (lg_block_csc), built by the trainer extension")
+ap.add_argument("--server-csc", action="store_true", help="with --csc: the SERVER builds the blocks (LEGION_EMIT_CSC=1) and get_next_csc returns views")
 args = ap.parse_args()
 
 import torch
@@ -46,7 +47,7 @@ for f in os.listdir("/dev/shm"):
         os.unlink(os.path.join("/dev/shm", f))
 BIN = os.path.join(ROOT, "sampling_server", "build", "bin", "sampling_server")
 t0 = time.time()
-proc = subprocess.Popen([BIN, "1", "0.0"], cwd=cwd, env=dict(os.environ, LEGION_SEED=str(bench.SEED)), stdout=subprocess.PIPE,
+proc = subprocess.Popen([BIN, "1", "0.0"], cwd=cwd, env=dict(os.environ, LEGION_SEED=str(bench.SEED), LEGION_EMIT_CSC="1" if args.server_csc else "0"), stdout=subprocess.PIPE,
                         stderr=subprocess.STDOUT, text=True)
 head = []
 while True:
@@ -64,9 +65,6 @@ steps = ipc_service.get_steps()
 train_steps, valid_steps, test_steps = [int(x) for x in steps]
 max_step = (train_steps + valid_steps) * args.epochs + test_steps
 bb = None
-if args.csc:
-    from legion_b200.blocks import BlockBuilder
-    bb = BlockBuilder(int(B * (fanout[0] + fanout[0] * fanout[1])) if len(fanout) == 2 else 8_000_000)
 H = len(fanout)
 t_train, n_train, rows, edges = 0.0, 0, 0, 0
 g = 0
@@ -74,13 +72,11 @@ for ep in range(args.epochs):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for s in range(train_steps):
-        out = ipc_service.get_next(D)
+        out = ipc_service.get_next_csc(D) if args.csc else ipc_service.get_next(D)  # csc: (indptr, indices, eids) per block
         sizes = ipc_service.get_block_size()
-        if bb is not None:
-            for k in range(H):
-                bb.csc(out[3 + 2 * k], out[4 + 2 * k], sizes[2 * k + 1])
-            torch.cuda.synchronize()
-        rows += out[0].numel(); edges += out[3].numel()
+        if args.csc:
+            torch.cuda.synchronize()  # the blocks are built on this process's stream: wait for them like a layer would
+        rows += out[0].numel(); edges += out[4 if args.csc else 3].numel()
         ipc_service.synchronize()
         g += 1
     t_train += time.perf_counter() - t1
@@ -89,12 +85,15 @@ for ep in range(args.epochs):
         ipc_service.get_next(D); ipc_service.synchronize(); g += 1
 for s in range(test_steps):
     ipc_service.get_next(D); ipc_service.synchronize(); g += 1
+from_host = bool(ipc_service.counters_from_host())
+csc_server = bool(ipc_service.csc_from_server())
 ipc_service.finalize()
 tail, _ = proc.communicate(timeout=120)
 assert proc.returncode == 0 and "Server Stopped" in tail, tail[-2000:]
 caps = [l.strip() for l in head if "capacity" in l or "Alpha" in l or "Preprocessing" in l]
+telemetry = [json.loads(l)["legion_b200_telemetry"] for l in tail.splitlines() if l.startswith('{"legion_b200_telemetry"')]
 print(json.dumps({"what": "sampling_server binary -> simpleIPCshm/semaphores/CUDA IPC -> ipc_service consumer (1 GPU)",
                   "workload": shape["name"], "num_nodes": N, "num_edges": E, "feature_dim": D, "batch": B, "fanout": fanout,
                   "train_steps_per_epoch": train_steps, "epochs": args.epochs, "seeds_per_s": n_train * B / t_train,
                   "ms_per_batch": 1e3 * t_train / n_train, "rows_per_batch": rows / n_train, "edges_per_batch": edges / n_train,
-                  "consumer_builds_csc": bool(args.csc), "server_ready_s": round(t_ready, 1), "server_says": caps}))
+                  "consumer_builds_csc": bool(args.csc), "counters_from_host": from_host, "csc_built_by_server": csc_server, "server_ready_s": round(t_ready, 1), "server_says": caps, "tier_telemetry": telemetry}))

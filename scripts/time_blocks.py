@@ -43,4 +43,14 @@ for h in range(H, 0, -1):
     o, t = ours(), torch_route()
     res["identical"] = bool(torch.equal(o[0].long(), t[0]) and torch.equal(o[1], t[1]) and torch.equal(o[2].long(), t[2]))
     out[f"block{h}"] = dict(edges=e, num_dst=num_dst, **res)
+# all blocks of the batch in one set of launches, sizes read on the device (lg_block_csc_batch: what the server runs)
+max_edges, max_dst, per, nodes, edges = [], [], B, B, 0
+for f in fanout:
+    max_dst.append(nodes); per *= f; edges += per; nodes += per; max_edges.append(edges)
+for _ in range(3): bb.csc_batch(buf.c, H, max_edges, max_dst)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); a.record()
+for _ in range(20): bb.csc_batch(buf.c, H, max_edges, max_dst)
+b.record(); torch.cuda.synchronize()
+out["all_blocks_one_call_us"] = round(a.elapsed_time(b) * 1000 / 20, 1)
 print(json.dumps(out))

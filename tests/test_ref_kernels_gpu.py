@@ -275,3 +275,61 @@ def test_reference_tail_batch_stride(ref, oracle):
         else:
             assert np.array_equal(mine["ids"][:44], ids[256:300])
     del tab
+
+
+COST_CASES = [
+    # N, avg deg, dim, cache bytes per GPU, Kg, train_step, pcie counters (topo transactions)
+    (6000, 10.0, 16, 200_000, 1, 30, (0, 0)),            # the reference's normal case: PCM counters are 0
+    (6000, 10.0, 16, 60_000, 2, 30, (0, 0)),
+    (6000, 10.0, 100, 300_000, 4, 12, (40_000, 2_000)),   # with topology transactions
+    (6000, 10.0, 128, 123_457, 8, 7, (5_000_000, 0)),
+    (3000, 6.0, 16, 40_000_000, 1, 30, (1000, 0)),        # degenerate: cache > dataset (cache/cache.cu:528-549)
+    (3000, 6.0, 16, 40_000_000, 4, 30, (0, 0)),
+]
+
+
+@pytest.mark.parametrize("case", COST_CASES)
+def test_cost_model_equals_reference(ref, oracle, case):
+    """UnifiedCache::CandidateSelection + CostModel (cache/cache.cu:360-551), run through the reference class itself
+    (oracle/ref_ops.cu: ref_cost_model), against lgo_cost_model (oracle) and lg_cost_model (the library)."""
+    N, avg, dim, cache_bytes, kg, train_step, counters = case
+    indptr, indices = small_graph(N, avg, 300)
+    N = len(indptr) - 1
+    rng = np.random.default_rng(N + kg)
+    # distinct aggregate hotness per vertex, so that the ranking does not depend on how ties are broken
+    # (thrust's sort is unstable, cache/cache.cu:415; ours breaks ties by vertex id)
+    base_n = rng.permutation(N).astype(np.uint64) * np.uint64(kg) * np.uint64(3)
+    base_e = rng.permutation(N).astype(np.uint64) * np.uint64(kg) * np.uint64(5)
+    node_hot = [(base_n // np.uint64(kg)) + np.uint64(j == 0) * (base_n % np.uint64(kg)) for j in range(kg)]
+    edge_hot = [(base_e // np.uint64(kg)) + np.uint64(j == 0) * (base_e % np.uint64(kg)) for j in range(kg)]
+    node_hot = [np.ascontiguousarray(x, np.uint64) for x in node_hot]
+    edge_hot = [np.ascontiguousarray(x, np.uint64) for x in edge_hot]
+    assert np.array_equal(sum(node_hot), base_n) and np.array_equal(sum(edge_hot), base_e)
+    max_ids = np.asarray(rng.integers(1000, 5000, kg), np.int32)
+    arr = lambda xs: (C.c_void_p * len(xs))(*[x.ctypes.data for x in xs])  # noqa: E731
+    ncap, ecap = C.c_int32(), C.c_int32()
+    QF, QT = np.zeros(N, np.int32), np.zeros(N, np.int32)
+    AF, AT = np.zeros(N, np.uint64), np.zeros(N, np.uint64)
+    ref.ref_cost_model.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    rc = ref.ref_cost_model(N, dim, cache_bytes, kg, train_step, arr(node_hot), arr(edge_hot), max_ids.ctypes.data,
+                            indptr.ctypes.data, counters[0], counters[1], C.addressof(ncap), C.addressof(ecap),
+                            QF.ctypes.data, QT.ctypes.data, AF.ctypes.data, AT.ctypes.data)
+    assert rc == 0
+    # CandidateSelection: the reference's ranking equals ours (hotness descending; no ties here)
+    o_order_n, o_sorted_n = oracle.hotness_rank(base_n)
+    o_order_e, o_sorted_e = oracle.hotness_rank(base_e)
+    assert np.array_equal(QF, o_order_n) and np.array_equal(AF, o_sorted_n)
+    assert np.array_equal(QT, o_order_e) and np.array_equal(AT, o_sorted_e)
+    # CostModel inputs as the reference forms them (cache/cache.cu:459-463)
+    topo_trans = counters[0] + counters[1]
+    feat_trans = sum((int(m) * train_step * dim * 4) // 64 for m in max_ids)
+    want = (ncap.value, ecap.value)
+    got_o = oracle.cost_model(o_sorted_n, o_sorted_e, o_order_e, indptr, dim, cache_bytes, kg, topo_trans, feat_trans)
+    assert got_o[:2] == want, (got_o, want)
+    L = capi.load()
+    a, b, al = C.c_int32(), C.c_int32(), C.c_double()
+    assert L.lg_cost_model(o_sorted_n.ctypes.data, o_sorted_e.ctypes.data, o_order_e.ctypes.data, indptr.ctypes.data, N, dim,
+                           cache_bytes, kg, topo_trans, feat_trans, C.byref(a), C.byref(b), C.byref(al)) == 0
+    assert (a.value, b.value) == want
