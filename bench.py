@@ -218,7 +218,7 @@ class Ctx:
 def setup_workload(args, workload, rank, world, local, dist):
     import torch
     from legion_b200 import capi
-    from legion_b200.runner import DataPath, MappedHostBuffer
+    from legion_b200.runner import DataPath, SharedHostBuffer
 
     c = Ctx()
     c.args, c.rank, c.world, c.local, c.dist = args, rank, world, local, dist
@@ -244,20 +244,29 @@ def setup_workload(args, workload, rank, world, local, dist):
     if c.topo_host:
         # full CSR in cudaHostAllocMapped memory, read by the sampler through UVA (storage/storage_management.cu:100-115,
         # engine/operator_impl.cu:224-243); the device copy only feeds presampling/placement and is dropped afterwards
-        c.h_ip, c.h_ix = MappedHostBuffer((N + 1) * 8), MappedHostBuffer(max(c.E, 1) * 4)
-        capi.check(dp.L.lg_memcpy_d2h(C.c_void_p(c.h_ip.host_ptr), C.c_void_p(c.ip.data_ptr()), (N + 1) * 8, dp._stream()))
-        capi.check(dp.L.lg_memcpy_d2h(C.c_void_p(c.h_ix.host_ptr), C.c_void_p(c.ix.data_ptr()), c.E * 4, dp._stream()))
+        # (one copy per box: every rank writes its slice of the arrays from its identical device copy)
+        dd = dist if world > 1 else None
+        c.h_ip = SharedHostBuffer((N + 1) * 8, rank, world, dd, "indptr")
+        c.h_ix = SharedHostBuffer(max(c.E, 1) * 4, rank, world, dd, "indices")
+        for hb, t, n_el, item in ((c.h_ip, c.ip, N + 1, 8), (c.h_ix, c.ix, c.E, 4)):
+            lo, hi = n_el * rank // world, n_el * (rank + 1) // world
+            hb.copy_from_device(t.data_ptr() + lo * item, lo * item, (hi - lo) * item, dp._stream())
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         c.host_keep += [c.h_ip, c.h_ix]
     dp.set_full_graph(c.ip.data_ptr(), c.ix.data_ptr(), keep=[c.ip, c.ix])  # topology replicated in each GPU's HBM
     c.feat_host = args.cache_ratio < 1.0
     if c.feat_host:
         # backing matrix in pinned host memory (cache/cache_impl.cuh:262-266 reads misses through UVA)
-        h_feat = MappedHostBuffer(N * D * 4)
-        for r0 in range(0, N, 1 << 22):  # generated by the device straight into the mapped allocation
-            capi.check(dp.L.lg_synth_features(dp._stream(), r0, min(1 << 22, N - r0), D, SEED,
+        h_feat = SharedHostBuffer(N * D * 4, rank, world, dist if world > 1 else None, "features")
+        lo, hi = N * rank // world, N * (rank + 1) // world  # each rank generates its share of the rows
+        for r0 in range(lo, hi, 1 << 22):  # generated by the device straight into the mapped allocation
+            capi.check(dp.L.lg_synth_features(dp._stream(), r0, min(1 << 22, hi - r0), D, SEED,
                                               C.c_void_p(h_feat.dev_ptr + r0 * D * 4)))
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         c.host_keep.append(h_feat)
         dp.set_backing_features(h_feat.dev_ptr, keep=[h_feat])
     elif c.feat is not None:
@@ -293,6 +302,7 @@ def setup_workload(args, workload, rank, world, local, dist):
             dp.build_topology_cache(order_t, c.topo_cap, kg=kg_t, j=rank % kg_t, dist=dist if world > 1 else None)
             del order_t
         dp.repoint_full_graph(c.h_ip.dev_ptr, c.h_ix.dev_ptr, drop=[c.ip, c.ix])
+        c.ip = c.ix = None  # the HBM copy of the CSR is gone from here on
     c.max_ids = int(mx.item())
     c.feature_rows = min(dp.num_ids, int(c.max_ids * 1.2) + 1)  # engine/server.cu:277
     del scratch, eh, nh
@@ -690,9 +700,13 @@ def run_workload(args, workload, rank, world, local, dist, steps, warmup, main_l
     # --- parity self-check against the CPU oracle (untimed; every rank; fails the run on mismatch) ---
     parity = None
     host_csr = None
-    if args.parity_check and not c.topo_host:
+    if args.parity_check:
         t0 = time.time()
-        host_csr = HostCSR(c.ip, c.ix, c.N, c.E, rank, world, dist)
+        if c.topo_host:  # the CSR the sampler reads through UVA is the host copy already
+            host_csr = Ctx()
+            host_csr.indptr, host_csr.indices = c.h_ip.numpy(np.int64, (c.N + 1,)), c.h_ix.numpy(np.int32, (c.E,))
+        else:
+            host_csr = HostCSR(c.ip, c.ix, c.N, c.E, rank, world, dist)
         run_steps(c, 0, 2)  # warm
         torch.cuda.synchronize()
         parity = parity_selfcheck(c, host_csr, step=warmup + steps + 7)
@@ -758,7 +772,7 @@ def run_workload(args, workload, rank, world, local, dist, steps, warmup, main_l
     # --- CPU baseline beside it (rank 0, N=1 only) ---
     if rank == 0 and world == 1 and main_line and not args.no_cpu_baseline:
         try:
-            if host_csr is None:
+            if host_csr is None and not c.topo_host:
                 host_csr = HostCSR(c.ip, c.ix, c.N, c.E, rank, world, dist)
             out["cpu_baseline"] = cpu_arm(c.shape, host_csr.indptr, host_csr.indices, c.my_train, steps=args.cpu_steps,
                                           warmup=1)["cpu_baseline"]

@@ -352,8 +352,9 @@ int lg_vmm_import(int32_t shareable_fd, int64_t bytes, void** ptr);
 int lg_vmm_free(void* ptr);
 int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t bytes); /* cudaHostAllocMapped */
 int lg_host_free(void* host_ptr);
-/* page-lock memory the host already owns (a POSIX shm mapping) so that asynchronous copies into it stay asynchronous */
-int lg_host_register(void* host_ptr, int64_t bytes);
+/* page-lock and map memory the host already owns (a POSIX shm mapping shared by the processes of a box): asynchronous
+ * copies into it stay asynchronous, and kernels can read it through *device_ptr (UVA; may be NULL when not needed) */
+int lg_host_register(void* host_ptr, int64_t bytes, void** device_ptr);
 int lg_host_unregister(void* host_ptr);
 int lg_ipc_export(const void* device_ptr, unsigned char handle[64]);
 int lg_ipc_open(const unsigned char handle[64], void** device_ptr);

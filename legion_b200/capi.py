@@ -105,7 +105,7 @@ _PROTOS = {
     "lg_vmm_free": (C.c_int, [vp]),
     "lg_host_alloc_mapped": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_int64]),
     "lg_host_free": (C.c_int, [vp]),
-    "lg_host_register": (C.c_int, [vp, C.c_int64]),
+    "lg_host_register": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
     "lg_host_unregister": (C.c_int, [vp]),
     "lg_ipc_export": (C.c_int, [vp, C.c_char * 64]),
     "lg_ipc_open": (C.c_int, [C.c_char * 64, C.POINTER(vp)]),

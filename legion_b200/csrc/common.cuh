@@ -107,19 +107,31 @@ __device__ __forceinline__ int32_t pick_neighbor(uint32_t slot, int32_t deg, uin
 }
 
 // ---- programmatic dependent launch (PDL).  Every kernel of the per-batch chain starts with pdl_prologue():
-//      griddepcontrol.wait blocks until every kernel before it in the stream has completed and flushed; then the
-//      NEXT kernel of the stream is allowed to become resident (griddepcontrol.launch_dependents) — it blocks in its
-//      own wait until this grid is done, so stream order holds for memory and only the launch latency between
-//      dependent kernels disappears.  The gpu-scope fence after the wait is NOT optional: it invalidates this SM's L1
-//      (CCTL.IVALL).  A PDL grid is dispatched — and the launch-time L1 invalidation happens — while its parent still
-//      runs; CTAs of the parent on the same SM keep filling L1 with sectors (counters, position-map words) that other
-//      CTAs of the parent rewrite later, and a plain load after the wait would hit those stale sectors (seen on the
-//      GPU: hotness_measure_kernel read the previous hop's nc[7]).  Without the launch attribute (LG_PDL=0, or a
-//      kernel launched with <<<>>>) wait and launch_dependents are no-ops. ----
+//      griddepcontrol.wait blocks until every kernel before it in the stream has completed and its memory operations
+//      are performed; then the NEXT kernel of the stream is allowed to become resident
+//      (griddepcontrol.launch_dependents) — it blocks in its own wait until this grid is done, so stream order holds
+//      for memory and only the launch latency between dependent kernels disappears.
+//      The fence.acq_rel.gpu after the wait is the ACQUIRE side of that hand-over in the PTX memory model: loads that
+//      follow an acquire fence may not return values older than what the synchronisation made visible, which on this
+//      hardware means the SM's L1 is invalidated (SASS: CCTL.IVALL) — a PDL grid is dispatched, and its launch-time
+//      invalidation happens, while its parent still runs and keeps filling L1 on the same SM.  Without the fence a
+//      plain load hit such a sector (seen on the GPU: hotness_measure_kernel read the previous hop's nc[7]).
+//      Belt and braces on top of the fence: the words a kernel's control flow depends on — the batch's counters — are
+//      read with ld.relaxed.gpu (ld_counter below: always served by L2, never by a possibly stale L1 line); the
+//      position-map lookups keep their L1-cached loads (hub words are re-read thousands of times per kernel) and rely
+//      on the acquire fence alone.  Without the launch attribute (LG_PDL=0, or a kernel launched with <<<>>>) wait and
+//      launch_dependents are no-ops and the kernel boundary itself invalidates L1. ----
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __threadfence();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// counters written by an earlier kernel of the chain (node_counter / edge_counter words): L2-coherent load
+__device__ __forceinline__ int32_t ld_counter(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // ---- relaxed gpu-scope 64-bit accesses (cross-CTA flags and dedup-table words) ----

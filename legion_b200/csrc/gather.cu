@@ -40,9 +40,9 @@ __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int
   if (a.nc) {
     // rows of hop h are [nc[9+h-1], nc[9+h]) — identical to (nc[0], nc[1]) right after op 3h
     // (engine/operator_impl.cu:65-81) but immutable afterwards, so a later hop may already run.
-    int32_t lo = a.hop == 0 ? 0 : a.nc[LG_INTRABATCH_CON * 3 + a.hop - 1];
-    int32_t hi = a.nc[LG_INTRABATCH_CON * 3 + a.hop];
-    int32_t first = a.hop_lo == 0 ? 0 : a.nc[LG_INTRABATCH_CON * 3 + a.hop_lo - 1];
+    int32_t lo = a.hop == 0 ? 0 : ld_counter(a.nc + LG_INTRABATCH_CON * 3 + a.hop - 1);
+    int32_t hi = ld_counter(a.nc + LG_INTRABATCH_CON * 3 + a.hop);
+    int32_t first = a.hop_lo == 0 ? 0 : ld_counter(a.nc + LG_INTRABATCH_CON * 3 + a.hop_lo - 1);
     *off = first;
     *cnt = hi - first;
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the op's counter_update (:83-85): snapshot of hop `hop`

@@ -314,14 +314,59 @@ extern "C" int lg_host_alloc_mapped(void** host_ptr, void** device_ptr, int64_t 
   if (device_ptr) LG_CUDA(cudaHostGetDevicePointer(device_ptr, *host_ptr, 0));
   return 0;
 }
-extern "C" int lg_host_register(void* host_ptr, int64_t bytes) {
+// Large regions are registered in chunks (one cudaHostRegister of tens of GB of shared-memory pages fails on some
+// kernels / hypervisors); with unified addressing a registered host pointer IS its device pointer, so the chunks still
+// form one contiguous device range — checked chunk by chunk.
+namespace {
+struct RegRegion {
+  void* p;
+  size_t bytes, chunk;
+};
+std::mutex g_reg_mu;
+std::vector<RegRegion> g_reg;
+}  // namespace
+extern "C" int lg_host_register(void* host_ptr, int64_t bytes, void** device_ptr) {
   LG_REQUIRE(host_ptr && bytes > 0, "lg_host_register: bad argument");
-  LG_CUDA(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable));
+  size_t chunk = (size_t)1 << 30;
+  if (const char* e = getenv("LG_HOST_REGISTER_CHUNK_MB")) chunk = (size_t)atoll(e) << 20;
+  if (chunk == 0 || chunk > (size_t)bytes) chunk = (size_t)bytes;
+  char* base = (char*)host_ptr;
+  for (size_t off = 0; off < (size_t)bytes; off += chunk) {
+    const size_t n = off + chunk <= (size_t)bytes ? chunk : (size_t)bytes - off;
+    cudaError_t e = cudaHostRegister(base + off, n, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    void* d = nullptr;
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d, base + off, 0);
+    if (e == cudaSuccess && d != (void*)(base + off)) e = cudaErrorNotSupported;  // no unified host/device addressing
+    if (e != cudaSuccess) {
+      for (size_t o2 = 0; o2 < off; o2 += chunk) cudaHostUnregister(base + o2);
+      if (d) cudaHostUnregister(base + off);
+      cudaGetLastError();
+      return lg_set_error("lg_host_register: chunk at +%zu MB of %lld MB -> %s", off >> 20, (long long)(bytes >> 20),
+                          cudaGetErrorString(e));
+    }
+  }
+  {
+    std::lock_guard<std::mutex> g(g_reg_mu);
+    g_reg.push_back({host_ptr, (size_t)bytes, chunk});
+  }
+  if (device_ptr) *device_ptr = host_ptr;
   return 0;
 }
 extern "C" int lg_host_unregister(void* host_ptr) {
   LG_REQUIRE(host_ptr, "lg_host_unregister: null");
-  LG_CUDA(cudaHostUnregister(host_ptr));
+  RegRegion r{nullptr, 0, 0};
+  {
+    std::lock_guard<std::mutex> g(g_reg_mu);
+    for (size_t i = 0; i < g_reg.size(); i++)
+      if (g_reg[i].p == host_ptr) {
+        r = g_reg[i];
+        g_reg.erase(g_reg.begin() + i);
+        break;
+      }
+  }
+  LG_REQUIRE(r.p, "lg_host_unregister: pointer was not registered through lg_host_register");
+  for (size_t off = 0; off < r.bytes; off += r.chunk) cudaHostUnregister((char*)host_ptr + off);
+  cudaGetLastError();
   return 0;
 }
 extern "C" int lg_host_free(void* host_ptr) {

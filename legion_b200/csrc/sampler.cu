@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kBlock) seed_local_kernel(const int32_t* __res
   pdl_prologue();
   const u64 keep = l2_policy((l2 & 4) ? 1 : 0);
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nc[1]) return;
+  if (i >= ld_counter(nc + 1)) return;
   const int32_t v = ids[i];
   seed_local[i] = v >= 0 ? (int32_t)map_lookup<true>(map, (uint32_t)v, keep) : 0;
 }
@@ -258,9 +258,10 @@ __device__ __forceinline__ bool sample_tile(const SampleArgs& a, const SampleHop
   const int tid = threadIdx.x;
   const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0), once = l2_policy((a.l2 & 8) ? 2 : 0);
   const bool first_hop = (h.hop == 1);
-  const int32_t F = first_hop ? a.nc[1] : a.ec[1];          // :201-206
-  const int32_t prev_edge_off = a.ec[0];
-  const int32_t edge_base = a.ec[0] + a.ec[1];              // :275
+  const int32_t ec0 = ld_counter(a.ec), ec1 = ld_counter(a.ec + 1);
+  const int32_t F = first_hop ? ld_counter(a.nc + 1) : ec1;  // :201-206
+  const int32_t prev_edge_off = ec0;
+  const int32_t edge_base = ec0 + ec1;                       // :275
   const int tslot = (h.hop - 1) * 2;
   if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
   const int n_tiles = (F + TILE_F - 1) / TILE_F;
@@ -489,9 +490,9 @@ __device__ __forceinline__ bool rank_tile(const RankArgs& a, const RankHop& h, c
   constexpr int TILE = kBlock * ITEMS;
   const int tid = threadIdx.x;
   const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0);
-  const int32_t E = a.ec[2];
-  const int32_t node_base = a.nc[0] + a.nc[1];  // :268
-  const int32_t edge_base = a.ec[0] + a.ec[1];  // :275 (the counters move on when every tile is done)
+  const int32_t E = ld_counter(a.ec + 2);
+  const int32_t node_base = ld_counter(a.nc) + ld_counter(a.nc + 1);  // :268
+  const int32_t edge_base = ld_counter(a.ec) + ld_counter(a.ec + 1);  // :275 (the counters move on when every tile is done)
   const int tslot = (h.hop - 1) * 2 + 1;
   if (tid == 0) trace_mark(a.trace, tslot, tile, 0);
   const int n_tiles = (E + TILE - 1) / TILE;
@@ -632,8 +633,8 @@ __device__ __forceinline__ void release_map(const ReleaseArgs& r) {
     for (int64_t i = t; i < r.n16; i += nt) r.fill[i] = ones;
   } else if (r.pm) {
     const u64 keep = l2_policy((r.l2 & 4) ? 1 : 0);
-    int32_t n = r.nc[LG_INTRABATCH_CON * 2 + 1];
-    const int32_t seeds = r.nc[LG_INTRABATCH_CON * 3];
+    int32_t n = ld_counter(r.nc + LG_INTRABATCH_CON * 2 + 1);
+    const int32_t seeds = ld_counter(r.nc + LG_INTRABATCH_CON * 3);
     if (seeds > n) n = seeds;  // before the first hop nc[7] is still 0
     for (int64_t i = t; i < n; i += nt) {
       const int32_t v = r.ids[i];
@@ -650,7 +651,7 @@ __device__ __forceinline__ void release_map(const ReleaseArgs& r) {
 // After the last hop nobody reads the position map again: lg_run_batch lets this kernel release it (`rel`).
 __device__ __forceinline__ void relabel_body(int32_t* __restrict__ agg_src, const int32_t* __restrict__ ec, int64_t t,
                                              int64_t n_threads) {
-  const int32_t off = ec[0], E = ec[1];
+  const int32_t off = ld_counter(ec), E = ld_counter(ec + 1);
   for (int64_t q0 = t * 4; q0 < E; q0 += n_threads * 4) {
     const int32_t p0 = (int32_t)q0;
     int32_t x[4], y[4];
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
                                                                  const int32_t* __restrict__ nc, u64* node_hot,
                                                                  int32_t* max_ids) {
   pdl_prologue();
-  const int32_t n = nc[LG_INTRABATCH_CON * 2 + 1];
+  const int32_t n = ld_counter(nc + LG_INTRABATCH_CON * 2 + 1);
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int32_t cid = ids[i];
     if (cid >= 0) atomicAdd(node_hot + cid, 1ull);
@@ -911,6 +912,17 @@ extern "C" int lg_sampler_create(int32_t device, int32_t max_batch, const int32_
   LG_REQUIRE(num_nodes >= 1 && num_nodes < (1ll << 31), "lg_sampler_create: num_nodes %lld outside [1, 2^31)",
              (long long)num_nodes);
   LG_CUDA(cudaSetDevice(device));
+  {  // L2 set-aside for the accesses that carry an evict_last policy (position map / dedup table, directories, indptr):
+     // LG_L2_PERSIST_MB, default 0 = the driver's default (no set-aside).  Measured: see profiles/r02_l2_persist.md
+    static const int mb = [] {
+      const char* e = getenv("LG_L2_PERSIST_MB");
+      return e ? atoi(e) : 0;
+    }();
+    if (mb > 0) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)mb << 20);
+      cudaGetLastError();
+    }
+  }
   lg_sampler* s = new lg_sampler();
   memset(s, 0, sizeof(*s));
   const int rc = sampler_init(s, device, max_batch, fanout, n_hops, num_nodes);

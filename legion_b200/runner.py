@@ -142,6 +142,68 @@ class MappedHostBuffer:
             pass
 
 
+class SharedHostBuffer:
+    """One host copy of a large read-only array for all the ranks of a box: a /dev/shm file that every rank maps and
+    page-locks (lg_host_register), readable by the kernels through UVA like the reference's cudaHostAllocMapped arrays
+    (storage/storage_management.cu:108-109) — which live once in the reference's single server process.  The name is
+    unlinked as soon as every rank holds a mapping.  world == 1: a plain MappedHostBuffer."""
+
+    def __init__(self, nbytes, rank=0, world=1, dist=None, tag="buf"):
+        import mmap
+        import os
+        import time
+        self.L = capi.load()
+        self.nbytes = int(nbytes)
+        self._plain = None
+        if world == 1:
+            self._plain = MappedHostBuffer(self.nbytes)
+            self.host_ptr, self.dev_ptr = self._plain.host_ptr, self._plain.dev_ptr
+            return
+        tok = [f"/dev/shm/legion_b200_{tag}_{os.getpid()}_{int(time.time() * 1e3)}" if rank == 0 else None]
+        dist.broadcast_object_list(tok, src=0)
+        path = tok[0]
+        if rank == 0:
+            fd0 = os.open(path, os.O_RDWR | os.O_CREAT, 0o600)
+            os.posix_fallocate(fd0, 0, max(self.nbytes, 4096))  # the pages exist before anybody page-locks them
+            os.close(fd0)
+        dist.barrier()
+        fd = os.open(path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, max(self.nbytes, 4096))
+        os.close(fd)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(path)
+        buf = (C.c_char * self.nbytes).from_buffer(self._mm)
+        self.host_ptr = C.addressof(buf)
+        self._keep = buf
+        dp = C.c_void_p()
+        check(self.L.lg_host_register(C.c_void_p(self.host_ptr), self.nbytes, C.byref(dp)))
+        self.dev_ptr = dp.value
+
+    def numpy(self, dtype, shape):
+        n = int(np.prod(shape))
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(self.host_ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def copy_from_device(self, src_ptr, byte_off, nbytes, stream):
+        """device -> this buffer at byte_off; split at 1 GB boundaries (lg_host_register page-locks in 1 GB chunks and
+        one cudaMemcpy may not span two registrations)"""
+        chunk = 1 << 30
+        done = 0
+        while done < nbytes:
+            off = byte_off + done
+            n = min(nbytes - done, chunk - (off % chunk))
+            check(self.L.lg_memcpy_d2h(C.c_void_p(self.host_ptr + off), C.c_void_p(src_ptr + done), n, stream))
+            done += n
+
+    def free(self):
+        if self._plain is not None:
+            self._plain.free()
+        elif self.host_ptr:
+            self.L.lg_host_unregister(C.c_void_p(self.host_ptr))
+        self.host_ptr = None
+
+
 class BatchBuffers:
     """The seven IPC buffers of one (gpu, pipeline slot) — engine/ipc_service.cu:134-206."""
 

@@ -60,7 +60,7 @@ class CUDAIPCEnv : public IPCEnv {
     void* addr = mmap(0, sizeof(lg_ext_shm), PROT_READ | PROT_WRITE, MAP_SHARED, ext_fd_, 0);
     if (addr == MAP_FAILED) return;
     std::memset(addr, 0, sizeof(lg_ext_shm));
-    if (lg_host_register(addr, sizeof(lg_ext_shm)) != 0) {  // pageable would make the copies synchronous: do without
+    if (lg_host_register(addr, sizeof(lg_ext_shm), nullptr) != 0) {  // pageable would make the copies synchronous: do without
       munmap(addr, sizeof(lg_ext_shm));
       return;
     }
