@@ -338,7 +338,10 @@ def build_cache(c, kg, replicate_ratio):
     rep = min(int(N * max(replicate_ratio, 0.0)), cached_rows) if kg > 1 else 0
     cap = max(rep + (cached_rows - rep + kg - 1) // kg, 1)
     dd = dist if c.world > 1 else None
-    if c.feat is not None and not c.feat_host:
+    identity = bool(args.identity and kg == 1 and cached_rows >= N and not c.feat_host)
+    if identity:  # the cache holds every vertex on this GPU: rows at row index = vertex id, no directory (LG_CACHE_IDENTITY)
+        dp.build_feature_cache_identity(seed=SEED if c.feat is None else None)
+    elif c.feat is not None and not c.feat_host:
         dp.build_feature_cache(c.order, cap, kg=kg, j=c.rank % kg, dist=dd, replicate=rep)
     else:  # shards generated in place (paper-scale shapes: no [N x D] matrix in vertex order in HBM)
         dp.build_feature_cache_synth(c.order, cap, SEED, kg=kg, j=c.rank % kg, dist=dd, keep_backing=c.feat_host,
@@ -346,7 +349,9 @@ def build_cache(c, kg, replicate_ratio):
     for r, _, _ in c.runners[1:]:
         r.share_storage_from(dp)
     c.kg, c.rep, c.cap = kg, rep, cap
-    c.layout = (f"Kc={c.world // kg},Kg={kg}: feature table interleaved by hotness rank over {kg} GPU(s) per clique"
+    c.layout = ((f"Kc={c.world // kg},Kg=1: the whole feature table on every GPU, rows at row index = vertex id (no directory lookup)"
+                 if identity else
+                 f"Kc={c.world // kg},Kg={kg}: feature table interleaved by hotness rank over {kg} GPU(s) per clique")
                 + (f", hottest {rep} rows replicated on every GPU (hybrid placement)" if rep else "")
                 + (f", hottest {args.cache_ratio:.3f} of the rows in HBM ({cap} rows/GPU), the rest in pinned host memory (UVA)"
                    if c.feat_host else ", fully HBM-cached")
@@ -966,6 +971,9 @@ def main():
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight per GPU (own scratch + stream each)")
     ap.add_argument("--overlap", type=int, default=2, choices=[0, 1, 2],
                     help="0 one stream; 1 gathers overlap the next hop; 2 pipelined across the two batch slots")
+    ap.add_argument("--no-identity", dest="identity", action="store_false",
+                    help="Kg=1 with every row cached: keep the reference's hotness-rank placement + directory instead of storing "
+                         "the rows at row index = vertex id")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", dest="parity_check", action="store_false",

@@ -74,11 +74,17 @@ typedef struct lg_topology {
 /* Feature cache: replaces float** gpu_float_feature + cpu_float_features + node_map_
  * (cache/cache.cu:572-602, cache/cache_impl.cuh:239-272).  directory[v] = gidx =
  * part*shard_rows + row (cache_impl.cuh:104-109) or LG_CACHEMISS_FLAG. */
+/* lg_feature_cache.flags.  LG_CACHE_IDENTITY: shard[local_part] holds EVERY vertex's row at row index = vertex id (a cache
+ * at least as large as the dataset on one GPU — the normal case with 180 GB of HBM); the lookup needs no directory (the
+ * reference's FindFeat probe, cache/cache.cu:180-215, and the 64-byte DRAM granule it costs per row disappear) and every
+ * row counts as a local hit.  `directory` must be NULL.  Gathered features are the same bits either way. */
+#define LG_CACHE_IDENTITY 1
+
 typedef struct lg_feature_cache {
   int32_t n_parts;
   int32_t shard_rows; /* node_capacity_ (rows per shard) */
   int32_t dim;        /* float_feature_len */
-  int32_t reserved;
+  int32_t flags;      /* LG_CACHE_* */
   int64_t num_nodes;
   const float* shard[LG_MAX_DEVICE];
   const float* backing;     /* full [num_nodes x dim] matrix: host UVA pointer or HBM; may be NULL when the

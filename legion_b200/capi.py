@@ -16,6 +16,7 @@ RNG_MINSTD, RNG_PHILOX = 0, 1
 GATHER_AUTO, GATHER_LDG, GATHER_TMA = 0, 1, 2
 TRAINMODE, VALIDMODE, TESTMODE = 0, 1, 2
 TAIL_EXACT, TAIL_REFERENCE = 0, 1
+CACHE_IDENTITY = 1
 
 vp = C.c_void_p
 
@@ -26,7 +27,7 @@ class Topology(C.Structure):
 
 
 class FeatureCache(C.Structure):
-    _fields_ = [("n_parts", C.c_int32), ("shard_rows", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("n_parts", C.c_int32), ("shard_rows", C.c_int32), ("dim", C.c_int32), ("flags", C.c_int32),
                 ("num_nodes", C.c_int64), ("shard", vp * MAX_DEVICE), ("backing", vp), ("directory", vp)]
 
 

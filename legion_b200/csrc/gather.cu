@@ -59,6 +59,10 @@ __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int
 __device__ __forceinline__ const float* locate(const GatherArgs& a, int32_t id, int* t) {
   *t = -1;
   if (id < 0) return nullptr;  // -1 padding of a tail batch (cache_impl.cuh:263-264)
+  if (a.cache.flags & LG_CACHE_IDENTITY) {  // every row is resident at its own index: no directory
+    *t = 0;
+    return a.cache.shard[a.local_part] + (int64_t)(id % a.cache.num_nodes) * a.cache.dim;
+  }
   int32_t gidx = LG_CACHEMISS_FLAG;
   if (a.cache.directory && id < a.cache.num_nodes) gidx = a.cache.directory[id];
   if (gidx < 0) {  // miss -> backing matrix (cache_impl.cuh:262-266)
@@ -248,12 +252,18 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
     }
     return a.ids[off + r];
   };
+  const bool identity = (a.cache.flags & LG_CACHE_IDENTITY) != 0;
   auto load_loc = [&](int32_t id) -> int32_t {
+    if (identity) return id;  // the row index IS the vertex id (see form_ptr)
     if (id < 0 || !a.cache.directory || id >= a.cache.num_nodes) return LG_CACHEMISS_FLAG;
     return ld_nc_s32_hint(a.cache.directory + id, keep);
   };
   auto form_ptr = [&](int32_t id, int32_t gidx) -> const float* {
     if (id < 0) return nullptr;  // -1 padding / out of range rows are skipped (cache_impl.cuh:263-264)
+    if (identity) {
+      t0++;
+      return a.cache.shard[a.local_part] + (int64_t)(id % a.cache.num_nodes) * a.cache.dim;
+    }
     if (gidx < 0) {              // miss -> backing matrix (cache_impl.cuh:262-266)
       t2++;
       if (!a.cache.backing) {
@@ -428,6 +438,10 @@ int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) 
 int check_cache(const lg_feature_cache* c) {
   LG_REQUIRE(c, "feature cache descriptor is null");
   LG_REQUIRE(c->dim > 0, "feature cache: dim %d", c->dim);
+  if (c->flags & LG_CACHE_IDENTITY) {
+    LG_REQUIRE(!c->directory && c->n_parts >= 1, "feature cache: LG_CACHE_IDENTITY takes no directory and needs the shard");
+    return 0;
+  }
   LG_REQUIRE(c->backing || c->directory, "feature cache: neither a backing matrix nor a directory");
   LG_REQUIRE(c->n_parts >= 0 && c->n_parts <= LG_MAX_DEVICE, "feature cache: n_parts %d", c->n_parts);
   LG_REQUIRE(!c->directory || c->shard_rows > 0, "feature cache: directory without shard_rows");

@@ -243,7 +243,7 @@ struct SampleSmem {
 };
 
 // One tile of TILE_F frontier entries, by the whole CTA.  Returns false when `tile` is past the hop's last tile.
-template <int TILE_F, int RNG, bool HASHED>
+template <int TILE_F, int RNG, bool HASHED, int U_OVERRIDE = 0>
 __device__ __forceinline__ bool sample_tile(const SampleArgs& a, const SampleHop& h, const int tile, SampleSmem<TILE_F>& sm) {
   static_assert(TILE_F <= kBlock, "one thread per frontier entry of the tile");
   long long* const s_start = sm.start;
@@ -254,7 +254,7 @@ __device__ __forceinline__ bool sample_tile(const SampleArgs& a, const SampleHop
   int32_t* const s_flocal = sm.flocal;
   int32_t* const s_red = sm.red;
 
-  constexpr int U = HASHED ? kSlotUnrollHashed : kSlotUnroll;  // slots in flight per thread
+  constexpr int U = U_OVERRIDE ? U_OVERRIDE : (HASHED ? kSlotUnrollHashed : kSlotUnroll);  // slots in flight per thread
   const int tid = threadIdx.x;
   const u64 keep = l2_policy((a.l2 & 4) ? 1 : 0), once = l2_policy((a.l2 & 8) ? 2 : 0);
   const bool first_hop = (h.hop == 1);
@@ -451,7 +451,9 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
   pdl_prologue();
   if (threadIdx.x == 0) s_tile = atomicAdd(&a.h.hs->sample_ticket, 1);  // tiles are claimed in order (see block_exclusive_prefix)
   __syncthreads();
-  sample_tile<TILE_F, RNG, HASHED>(a, a.h, s_tile, sm);
+  // HASHED with a register cap (MINB >= 5: 51 / 40 registers): fewer slots in flight per thread, more CTAs per SM — the
+  // 782 tiles of a 200 k-entry frontier run as ONE wave (64 registers: 592 slots, 1.32 waves)
+  sample_tile<TILE_F, RNG, HASHED, (HASHED && MINB >= 5) ? 3 : 0>(a, a.h, s_tile, sm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -842,11 +844,12 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //   coalesced arrays, was measured and rejected: hop 1 +5 us, hop 2 -2 us)
 // (A forced shared-memory carve-out on these kernels, LG_CARVEOUT, was measured and rejected: profiles/r01b_overlap.md.)
 struct SamplerTune {
-  int sample_tile, sample_minb, rank_items, red_precheck, chain_ctas;
+  int sample_tile, sample_minb, rank_items, red_precheck, chain_ctas, sample_minb_hashed;
 };
 static const SamplerTune& sampler_tune() {
   static SamplerTune t = [] {
-    SamplerTune x{0, 6, 0, 1, kChainCtasPerSm};
+    SamplerTune x{0, 6, 0, 1, kChainCtasPerSm, 0};
+    if (const char* e = getenv("LG_SAMPLE_MINB_HASHED")) x.sample_minb_hashed = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_TILE")) x.sample_tile = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_MINB")) x.sample_minb = atoi(e);
     if (const char* e = getenv("LG_RANK_ITEMS")) x.rank_items = atoi(e);
@@ -1274,6 +1277,10 @@ static cudaError_t launch_sample(bool pdl, int tile_f, int grid, cudaStream_t st
     case 256:
       if (!HASHED && sampler_tune().sample_minb == 6)
         return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, false, 6>, grid, kBlock, 0, st, a);
+      if (HASHED && sampler_tune().sample_minb_hashed == 6)
+        return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, HASHED, 6>, grid, kBlock, 0, st, a);
+      if (HASHED && sampler_tune().sample_minb_hashed == 5)
+        return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, HASHED, 5>, grid, kBlock, 0, st, a);
       return lg_launch_opt(pdl, sample_hop_kernel<256, RNG, HASHED, 0>, grid, kBlock, 0, st, a);
     case 128: return lg_launch_opt(pdl, sample_hop_kernel<128, RNG, HASHED, 0>, grid, kBlock, 0, st, a);
     case 64: return lg_launch_opt(pdl, sample_hop_kernel<64, RNG, HASHED, 0>, grid, kBlock, 0, st, a);

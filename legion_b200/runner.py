@@ -307,8 +307,9 @@ class DataPath:
         self._keep.extend(keep)
         self._set_cache([], None, 0)
 
-    def _set_cache(self, shard_ptrs, directory, shard_rows):
+    def _set_cache(self, shard_ptrs, directory, shard_rows, flags=0):
         c = FeatureCache()
+        c.flags = int(flags)
         c.n_parts = len(shard_ptrs)
         c.shard_rows = int(shard_rows)
         c.dim = self.dim
@@ -380,6 +381,25 @@ class DataPath:
         self._set_cache(shard_ptrs, directory, cap)
         self.feat_shard = raw
         return directory
+
+    def build_feature_cache_identity(self, seed=None):
+        """A cache that holds every vertex on this GPU: rows stored at row index = vertex id, no directory
+        (LG_CACHE_IDENTITY).  seed given: the rows are generated in place from the synthetic feature function; else copied
+        from the backing matrix."""
+        st = self._stream()
+        raw = self._shard_alloc(self.N * self.dim * 4, 1)
+        if seed is not None:
+            for r0 in range(0, self.N, 1 << 24):
+                check(self.L.lg_synth_features(st, r0, min(1 << 24, self.N - r0), self.dim, seed,
+                                               C.c_void_p(raw.ptr + r0 * self.dim * 4)))
+        else:
+            check(self.L.lg_memcpy_d2d(C.c_void_p(raw.ptr), C.c_void_p(self._backing), self.N * self.dim * 4, st))
+        torch.cuda.current_stream().synchronize()
+        self._cache_keep = [raw]
+        self.local_part = 0
+        self._set_cache([raw.ptr], None, self.N, flags=capi.CACHE_IDENTITY)
+        self.feat_shard = raw
+        return None
 
     def build_topology_cache(self, order, cap, kg=1, j=0, ki=0, dist=None):
         """GraphCache (storage/graph_storage.cu:76-111) + topology directory (cache/cache.cu:116-129)"""

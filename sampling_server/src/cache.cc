@@ -128,12 +128,51 @@ static int32_t ReplicatedRows(int32_t ncap, int32_t kg) {
   return (int32_t)(r * ncap);
 }
 
+// A cache that holds EVERYTHING on one GPU (Kg = 1 and the capacity chosen by the cost model covers every vertex — the
+// normal case with 180 GB of HBM) needs no lookup structure at all: feature rows are stored at row index = vertex id
+// (LG_CACHE_IDENTITY) and the CSR is simply resident in HBM (slot P of the pointer table, no topology directory).  The
+// reference still builds and probes its three hash maps in that case (cache/cache.cu:80-136,180-225).
+// LEGION_IDENTITY=0 keeps the rank-ordered shards + directories.
+static bool IdentityEnabled() {
+  const char* e = std::getenv("LEGION_IDENTITY");
+  return !(e && std::atoi(e) == 0);
+}
+
 void UnifiedCache::FillUp(int, FeatureStorage* feature, GraphStorage* graph) {
   const int64_t n = feature->TotalNodeNum();
   const int32_t dim = feature->GetFloatFeatureLen();
   for (int32_t i = 0; i < Kc_; i++) {
     const int32_t ncap = node_capacity_[i], ecap = edge_capacity_[i];
     const int32_t rep = ReplicatedRows(ncap, Kg_);
+    if (Kg_ == 1 && IdentityEnabled() && ncap >= n && ecap >= n) {
+      const int32_t dev = i;
+      LGCHECK(lg_set_device(dev));
+      const int64_t n_edges = graph->HostIndptr()[n];
+      auto* rows = (float*)DevAlloc(n * dim * 4, false);
+      LGCHECK(lg_memcpy_d2d(rows, feature->GetAllFloatFeature(), n * dim * 4, nullptr));
+      auto* ip = (int64_t*)DevAlloc((n + 1) * 8, false);
+      auto* ix = (int32_t*)DevAlloc((n_edges > 0 ? n_edges : 1) * 4, false);
+      LGCHECK(lg_memcpy_d2d(ip, graph->GetCSRNodeIndexCPU(), (n + 1) * 8, nullptr));
+      LGCHECK(lg_memcpy_d2d(ix, graph->GetCSRNodeMatrixCPU(), n_edges * 4, nullptr));
+      LGCHECK(lg_stream_synchronize(nullptr));
+      lg_feature_cache& c = fcache_[dev];
+      c.n_parts = 1;
+      c.shard_rows = (int32_t)n;
+      c.dim = dim;
+      c.flags = LG_CACHE_IDENTITY;
+      c.num_nodes = n;
+      c.shard[0] = rows;
+      c.backing = feature->GetAllFloatFeature();
+      c.directory = nullptr;
+      lg_topology* t = graph->Topology(dev);
+      t->n_parts = 0;
+      t->shard_rows = 0;
+      t->indptr[0] = ip;
+      t->indices[0] = ix;
+      t->directory = nullptr;
+      std::cout << "Everything fits GPU " << dev << ": rows and CSR resident in HBM, no lookup directories" << std::endl;
+      continue;
+    }
     if (rep > 0) std::cout << "Replicated feature rows: " << rep << " of " << ncap << " per GPU on Clique: " << i << std::endl;
     std::vector<float*> shard(Kg_);
     std::vector<int64_t*> sip(Kg_);

@@ -163,3 +163,32 @@ def test_synth_device_generator_matches_numpy():
     lab = torch.empty(N, dtype=torch.int32, device="cuda:0")
     capi.check(L.lg_synth_labels(st, N, 47, lab.data_ptr()))
     assert np.array_equal(lab.cpu().numpy(), synth.labels(N, 47))
+
+
+@pytest.mark.parametrize("dim", [100, 128, 7])
+def test_identity_cache_needs_no_directory(dim):
+    """LG_CACHE_IDENTITY: every row resident at row index = vertex id — both movers, -1 padding, all rows counted local"""
+    from legion_b200.runner import DataPath
+    N = 50000
+    feat = synth.features(0, N, dim, 3)
+    d_feat = torch.from_numpy(feat).cuda()
+    dp = DataPath(0, [2], 8, N, dim)
+    dp.set_backing_features(d_feat.data_ptr(), keep=[d_feat])
+    dp.build_feature_cache_identity()
+    assert dp.cache.directory is None and dp.cache.flags == capi.CACHE_IDENTITY
+    rng = np.random.default_rng(dim)
+    ids = rng.integers(0, N, 30000).astype(np.int32)
+    ids[::97] = -1
+    d_ids = torch.from_numpy(ids).cuda()
+    for variant in (capi.GATHER_LDG, capi.GATHER_TMA):
+        out = torch.full((len(ids), dim), 7.0, dtype=torch.float32, device="cuda")
+        tiers = torch.zeros(3, dtype=torch.int64, device="cuda")
+        capi.check(dp.L.lg_gather_rows(dp._stream(), C.byref(dp.cache), C.c_void_p(d_ids.data_ptr()), len(ids),
+                                       C.c_void_p(out.data_ptr()), 0, variant, C.c_void_p(tiers.data_ptr())))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        ok = ids >= 0
+        assert np.array_equal(got[ok].view(np.uint32), feat[ids[ok]].view(np.uint32))
+        assert (got[~ok] == 7.0).all()
+        assert tiers.cpu().tolist() == [int(ok.sum()), 0, 0]
+    dp.close()
