@@ -214,6 +214,7 @@ struct SampleArgs {
   DedupMap map;
   u64* edge_hot;
   int32_t* status;        // sticky status word of the handle (4 = edge_dst holds an id outside [0, num_nodes))
+  int32_t persistent;     // the CTAs loop over tickets (grid smaller than the number of tiles)
   int32_t precheck;       // DENSE: L1-cached look at the map word before the RED.MIN (LG_RED_PRECHECK)
   uint32_t batch_id, stream_id, k0, k1;
   int32_t l2;  // lg_l2_hints()
@@ -449,11 +450,17 @@ __global__ void __launch_bounds__(kBlock, MINB) sample_hop_kernel(const SampleAr
   __shared__ SampleSmem<TILE_F> sm;
   __shared__ int32_t s_tile;
   pdl_prologue();
-  if (threadIdx.x == 0) s_tile = atomicAdd(&a.h.hs->sample_ticket, 1);  // tiles are claimed in order (see block_exclusive_prefix)
-  __syncthreads();
-  // HASHED with a register cap (MINB >= 5: 51 / 40 registers): fewer slots in flight per thread, more CTAs per SM — the
-  // 782 tiles of a 200 k-entry frontier run as ONE wave (64 registers: 592 slots, 1.32 waves)
-  sample_tile<TILE_F, RNG, HASHED, (HASHED && MINB >= 5) ? 3 : 0>(a, a.h, s_tile, sm);
+  // One tile per CTA (grid = tiles), or — LG_SAMPLE_CTAS_PER_SM=k — a grid of 148 x k CTAs that keep claiming tiles: the
+  // kernel then never holds more than k CTAs' worth of registers per SM, which is what leaves room for the gather's CTAs
+  // on every SM while both run (64 registers x 256 threads x 4 CTAs is the whole register file).
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.h.hs->sample_ticket, 1);  // tiles are claimed in order (see block_exclusive_prefix)
+    __syncthreads();
+    // HASHED with a register cap (MINB >= 5: 47 / 40 registers): fewer slots in flight per thread, more CTAs per SM
+    const bool more = sample_tile<TILE_F, RNG, HASHED, (HASHED && MINB >= 5) ? 3 : 0>(a, a.h, s_tile, sm);
+    if (!a.persistent || !more) break;
+    __syncthreads();  // the tile's shared memory and s_tile are free again
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -474,6 +481,7 @@ struct RankArgs {
   DedupMap map;
   int32_t ids_cap;
   int32_t l2;
+  int32_t persistent;
   int32_t* status;
   u64* trace;
   RankHop h;
@@ -599,9 +607,13 @@ __global__ void __launch_bounds__(kBlock) rank_kernel(const RankArgs a) {
   __shared__ int32_t s_tile, s_last;
   const int tid = threadIdx.x;
   pdl_prologue();
-  if (tid == 0) s_tile = atomicAdd(&a.h.hs->rank_ticket, 1);
-  __syncthreads();
-  rank_tile<ITEMS, HASHED, PUBLISH>(a, a.h, s_tile, s_red);
+  for (;;) {  // one tile per CTA, or (a.persistent) a smaller grid that keeps claiming tiles — see sample_hop_kernel
+    if (tid == 0) s_tile = atomicAdd(&a.h.hs->rank_ticket, 1);
+    __syncthreads();
+    const bool more = rank_tile<ITEMS, HASHED, PUBLISH>(a, a.h, s_tile, s_red);
+    if (!a.persistent || !more) break;
+    __syncthreads();
+  }
   // the last CTA to finish updates the counters
   __syncthreads();
   if (tid == 0) {
@@ -837,6 +849,11 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //                    the word already holds an earlier position (hub vertices: sample hop 2 0.0915 -> 0.0827 ms);
 //                    bit 1 = the same before the hashed layout's atomicMin (off: an earlier version measured +3 % on a
 //                    hub-heavy 2.4 M-vertex graph, -5 % at UK-Union scale — the regime the hashed layout is for)
+//   LG_SAMPLE_CTAS_PER_SM / LG_RANK_CTAS_PER_SM   (default 3 / 3; 0 = one tile per CTA) the long hops' sample and rank kernels
+//                    run as grids of 148 x k CTAs that keep claiming tiles.  Alone the kernels get slower (hop 2 of the
+//                    UK-Union shape 0.172 -> 0.199 ms), but they no longer fill the register files (64 registers x 256
+//                    threads x 4 CTAs = all of it), so the gather's CTAs of the other batches in flight find room on every
+//                    SM: pipelined +3.5 % (UK-Union shape) / +4.5 % (products shape), profiles/r02_persistent_grids.md
 //   LG_CHAIN         1 = lg_run_batch runs the dense layout's sampler chain as ONE persistent kernel (chain_kernel; read
 //                    when a handle is created).  Opt-in: bit-exact, but measured slower — 34.1 vs 40.8 M seeds/s at best,
 //                    profiles/r01d_chain_kernel.md.  LG_CHAIN_CTAS: its CTAs per SM.
@@ -844,11 +861,13 @@ __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* 
 //   coalesced arrays, was measured and rejected: hop 1 +5 us, hop 2 -2 us)
 // (A forced shared-memory carve-out on these kernels, LG_CARVEOUT, was measured and rejected: profiles/r01b_overlap.md.)
 struct SamplerTune {
-  int sample_tile, sample_minb, rank_items, red_precheck, chain_ctas, sample_minb_hashed;
+  int sample_tile, sample_minb, rank_items, red_precheck, chain_ctas, sample_minb_hashed, sample_ctas_per_sm, rank_ctas_per_sm;
 };
 static const SamplerTune& sampler_tune() {
   static SamplerTune t = [] {
-    SamplerTune x{0, 6, 0, 1, kChainCtasPerSm, 0};
+    SamplerTune x{0, 6, 0, 1, kChainCtasPerSm, 0, 3, 3};  // persistent grids of 3 CTAs per SM: profiles/r02_persistent_grids.md
+    if (const char* e = getenv("LG_SAMPLE_CTAS_PER_SM")) x.sample_ctas_per_sm = atoi(e);
+    if (const char* e = getenv("LG_RANK_CTAS_PER_SM")) x.rank_ctas_per_sm = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_MINB_HASHED")) x.sample_minb_hashed = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_TILE")) x.sample_tile = atoi(e);
     if (const char* e = getenv("LG_SAMPLE_MINB")) x.sample_minb = atoi(e);
@@ -1326,6 +1345,12 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   a.h.relabel_prev = relabel_prev ? 1 : 0;
   a.precheck = sampler_tune().red_precheck;
   a.status = s->status;
+  int sample_grid = s->sample_tiles[h];
+  a.persistent = 0;
+  if (sampler_tune().sample_ctas_per_sm > 0 && sample_grid > kSMs * sampler_tune().sample_ctas_per_sm) {
+    sample_grid = kSMs * sampler_tune().sample_ctas_per_sm;
+    a.persistent = 1;
+  }
   a.batch_id = batch_id;
   a.stream_id = stream_id;
   a.k0 = (uint32_t)rng_seed;
@@ -1333,11 +1358,11 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   a.l2 = lg_l2_hints();
   a.trace = s->trace;
   if (rng_kind == LG_RNG_MINSTD) {
-    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_MINSTD, true>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
-    else LG_CUDA((launch_sample<LG_RNG_MINSTD, false>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_MINSTD, true>(pdl_on(s), s->sample_tile_f[h], sample_grid, st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_MINSTD, false>(pdl_on(s), s->sample_tile_f[h], sample_grid, st, a)));
   } else {
-    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_PHILOX, true>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
-    else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(pdl_on(s), s->sample_tile_f[h], s->sample_tiles[h], st, a)));
+    if (s->hashed) LG_CUDA((launch_sample<LG_RNG_PHILOX, true>(pdl_on(s), s->sample_tile_f[h], sample_grid, st, a)));
+    else LG_CUDA((launch_sample<LG_RNG_PHILOX, false>(pdl_on(s), s->sample_tile_f[h], sample_grid, st, a)));
   }
   RankArgs r;
   r.h.gid = s->gid[h & 1];
@@ -1354,13 +1379,19 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
   r.l2 = lg_l2_hints();
   r.status = s->status;
   r.trace = s->trace;
+  int rank_grid = s->rank_tiles[h];
+  r.persistent = 0;
+  if (sampler_tune().rank_ctas_per_sm > 0 && rank_grid > kSMs * sampler_tune().rank_ctas_per_sm) {
+    rank_grid = kSMs * sampler_tune().rank_ctas_per_sm;
+    r.persistent = 1;
+  }
   const bool publish = hop < s->n_hops;  // a later hop inserts into / reads the map
   if (s->hashed) {
-    if (publish) LG_CUDA((launch_rank<true, true>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
-    else LG_CUDA((launch_rank<true, false>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
+    if (publish) LG_CUDA((launch_rank<true, true>(pdl_on(s), s->rank_items[h], rank_grid, st, r)));
+    else LG_CUDA((launch_rank<true, false>(pdl_on(s), s->rank_items[h], rank_grid, st, r)));
   } else {
-    if (publish) LG_CUDA((launch_rank<false, true>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
-    else LG_CUDA((launch_rank<false, false>(pdl_on(s), s->rank_items[h], s->rank_tiles[h], st, r)));
+    if (publish) LG_CUDA((launch_rank<false, true>(pdl_on(s), s->rank_items[h], rank_grid, st, r)));
+    else LG_CUDA((launch_rank<false, false>(pdl_on(s), s->rank_items[h], rank_grid, st, r)));
   }
   if (relabel_own) {
     const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
