@@ -494,8 +494,16 @@ extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache,
   if (rc) return rc;
   LG_REQUIRE(ids && dst, "lg_gather_rows: null argument");
   if (n <= 0) return 0;
-  static thread_local int32_t* dummy_status = nullptr;
-  if (!dummy_status) LG_CUDA(cudaMalloc(&dummy_status, sizeof(int32_t)));
+  // no handle to own a status word: one per (thread, device), zeroed when it is created
+  static thread_local int32_t* dummy_by_device[LG_MAX_DEVICE * 2] = {};
+  int dev = 0;
+  LG_CUDA(cudaGetDevice(&dev));
+  LG_REQUIRE(dev >= 0 && dev < LG_MAX_DEVICE * 2, "lg_gather_rows: device %d", dev);
+  if (!dummy_by_device[dev]) {
+    LG_CUDA(cudaMalloc(&dummy_by_device[dev], sizeof(int32_t)));
+    LG_CUDA(cudaMemset(dummy_by_device[dev], 0, sizeof(int32_t)));
+  }
+  int32_t* dummy_status = dummy_by_device[dev];
   GatherArgs a;
   a.cache = *cache;
   a.ids = ids;

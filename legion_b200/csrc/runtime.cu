@@ -191,9 +191,21 @@ int vmm_map(const Vmm& v, CUmemGenericAllocationHandle h, size_t bytes, int acce
 }
 }  // namespace
 
+// the length an allocation of `bytes` occupies: a multiple of the driver's RECOMMENDED granularity for device memory on the
+// current device (2 MB on B200) — the exporter and the importer both derive the mapped length from it, so they agree
+// whatever the granularity is
+static size_t vmm_granularity(Vmm& v, int dev) {
+  CUmemAllocationProp prop = vmm_prop(dev);
+  size_t gran = 0;
+  if (!v.ok || v.MemGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) gran = 2u << 20;
+  return gran;
+}
 extern "C" int64_t lg_vmm_round_up(int64_t bytes) {
-  const int64_t g = 2ll << 20;  // 2 MB: the allocation granularity of device memory on this architecture
-  return (bytes + g - 1) / g * g;
+  Vmm v;
+  int dev = 0;
+  size_t g = 2u << 20;
+  if (vmm_load(&v) == 0 && cudaGetDevice(&dev) == cudaSuccess) g = vmm_granularity(v, dev);
+  return (int64_t)(((size_t)bytes + g - 1) / g * g);
 }
 
 extern "C" int lg_vmm_alloc(int64_t bytes, void** ptr, int32_t* shareable_fd) {
@@ -204,12 +216,10 @@ extern "C" int lg_vmm_alloc(int64_t bytes, void** ptr, int32_t* shareable_fd) {
   int dev = 0;
   LG_CUDA(cudaGetDevice(&dev));
   CUmemAllocationProp prop = vmm_prop(dev);
-  size_t gran = 0;
-  CUresult r = v.MemGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
-  if (r != CUDA_SUCCESS || gran == 0) gran = 2u << 20;
+  const size_t gran = vmm_granularity(v, dev);
   const size_t len = ((size_t)bytes + gran - 1) / gran * gran;
   CUmemGenericAllocationHandle h;
-  r = v.MemCreate(&h, len, &prop, 0);
+  CUresult r = v.MemCreate(&h, len, &prop, 0);
   if (r != CUDA_SUCCESS) return lg_set_error("cuMemCreate(%zu bytes on device %d) -> %d", len, dev, (int)r);
   int fd = -1;
   r = v.MemExport(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
@@ -237,7 +247,8 @@ extern "C" int lg_vmm_import(int32_t shareable_fd, int64_t bytes, void** ptr) {
   CUmemGenericAllocationHandle h;
   CUresult r = v.MemImport(&h, (void*)(uintptr_t)shareable_fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
   if (r != CUDA_SUCCESS) return lg_set_error("cuMemImportFromShareableHandle(fd %d) -> %d", shareable_fd, (int)r);
-  const size_t len = (size_t)lg_vmm_round_up(bytes);
+  const size_t gran = vmm_granularity(v, dev);  // same rule as lg_vmm_alloc on the exporting GPU (same architecture)
+  const size_t len = ((size_t)bytes + gran - 1) / gran * gran;
   rc = vmm_map(v, h, len, dev, ptr);
   if (rc) v.MemRelease(h);
   return rc;

@@ -1394,7 +1394,14 @@ static int sample_hop(lg_sampler* s, cudaStream_t st, const lg_topology* topo, i
     else LG_CUDA((launch_rank<false, false>(pdl_on(s), s->rank_items[h], rank_grid, st, r)));
   }
   if (relabel_own) {
-    const int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
+    int64_t grid = (s->slots_per_hop[hop] + kBlock * 4 - 1) / (kBlock * 4);
+    {  // grid-stride kernel: LG_RELABEL_CTAS_PER_SM caps its footprint like the sample / rank kernels' (0 = one pass per thread)
+      static const int cap = [] {
+        const char* e = getenv("LG_RELABEL_CTAS_PER_SM");
+        return e ? atoi(e) : 0;
+      }();
+      if (cap > 0 && grid > (int64_t)kSMs * cap) grid = (int64_t)kSMs * cap;
+    }
     ReleaseArgs rel;
     memset(&rel, 0, sizeof(rel));
     if (release) rel = release_args(s, b);

@@ -1,13 +1,17 @@
 #!/bin/bash
 # end-of-round visit: what the driver runs (GPU tests, smoke, both bench arms) + the ncu evidence for profiles/
+# usage: TAG=r02 bash scripts/gpu_final.sh        (one GPU)
 set -u
-TAG=${TAG:-r01e}
+TAG=${TAG:-r02}
+SCALE=${SCALE:-0.25}   # ncu runs: UK-Union shape scaled so that kernel replay does not have to save/restore 100 GB
 mkdir -p gpurun_out
-echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest_gpu.log
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu -rs 2>&1 | tail -6 | tee gpurun_out/${TAG}_pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
-echo "== bench (default)"; timeout 900 python bench.py > gpurun_out/${TAG}_bench_products.json 2> gpurun_out/${TAG}_bench.err; tail -c 1500 gpurun_out/${TAG}_bench_products.json
-echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; tail -c 400 gpurun_out/${TAG}_bench_reference.json
-timeout 600 python bench.py --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/${TAG}_bench_serial.json 2>> gpurun_out/${TAG}_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-  python bench.py --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --no-server-e2e --inflight 1 --overlap 0 > gpurun_out/${TAG}_ncu_launch.log 2>&1
-TAG=$TAG bash scripts/gpu_ncu.sh > gpurun_out/${TAG}_ncu_table.txt 2>&1; cat gpurun_out/${TAG}_ncu_table.txt
+echo "== bench (default)"; timeout 900 python bench.py > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench.err; tail -c 600 gpurun_out/${TAG}_bench_default.json
+echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; tail -c 300 gpurun_out/${TAG}_bench_reference.json
+echo "== launch list (ncu)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gather_|sample_hop|rank_kernel|relabel_kernel|batch_generate|release_kernel|seed_local" -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
+  python bench.py --scale $SCALE --steps 3 --warmup 3 --presample 2 --no-cpu-baseline --no-extras --no-parity-check --inflight 1 --overlap 0 > gpurun_out/${TAG}_ncu_launch.log 2>&1
+echo "== full capture (ncu --set full)"
+TAG=$TAG SKIP=${SKIP:-42} COUNT=${COUNT:-16} BENCH_ARGS="--scale $SCALE" bash scripts/gpu_ncu.sh > gpurun_out/${TAG}_ncu_table.txt 2>&1; cat gpurun_out/${TAG}_ncu_table.txt
+timeout 300 python bench.py --scale $SCALE --steps 50 --no-cpu-baseline --no-extras --no-parity-check > gpurun_out/${TAG}_bench_scaled.json 2>> gpurun_out/${TAG}_bench.err
