@@ -919,6 +919,9 @@ static int pick_rank_items(int64_t edges_max, bool hashed) {
   if (edges_max <= 4ll * kBlock * kSMs * 5) return 4;
   const int o = sampler_tune().rank_items;
   if (o == 4 || o == 8 || o == 12 || o == 16) return o;
+  // persistent grid (LG_RANK_CTAS_PER_SM, default 3 CTAs per SM = 444): 8 edges per thread = 977 tiles of 2048 edges for a
+  // 2 M-edge hop, 2.2 rounds of small tiles instead of 1.1 rounds of large ones (profiles/r02_persistent_grids.md)
+  if (sampler_tune().rank_ctas_per_sm > 0) return 8;
   return hashed ? 16 : 12;
 }
 
