@@ -682,7 +682,10 @@ def roofline_of(c, res, hbm_peak, peak_kind, traffic_key):
              "frac": mix["frac_of_mix_roofline"],
              "bound_note": f"the gather of this hit mix is bound by {bound}: achieved = bytes that cross that link per launch / launch time"}
     tr = recorded_traffic(traffic_key)
-    r.update({"traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
+    traffic = None
+    if tr:  # the capture's bytes per gathered row x the rows of THIS launch (the capture may be of a scaled-down graph)
+        traffic = tr["bytes_per_row"] * rows if "bytes_per_row" in tr else tr["bytes_per_launch"]
+    r.update({"traffic": traffic, "traffic_source": tr["source"] if tr else None,
               "traffic_key": traffic_key, "peak_kind": peak_kind if bound == "hbm" else mix["peaks_source"][bound],
               "kernel": f"feature gather ({res['gather_launches_per_step']} launch(es) per step)",
               "algorithmic_bytes_per_step": alg, "rows_per_step": rows, "gather_ms_per_step": res["gather_ms_per_step"],

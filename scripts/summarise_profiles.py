@@ -24,7 +24,7 @@ for r in rows_of(launches):
     a = agg.setdefault(k, [0, 0.0])
     a[0] += 1
     a[1] += us
-ours = {k: v for k, v in agg.items() if "<unnamed>" in k or "lg::" in k}
+ours = {k: v for k, v in agg.items() if "<unnamed>" in k or "lg::" in k or "seed_local" in k or "relabel" in k}
 step = {k: v for k, v in ours.items() if any(s in k for s in ("gather_", "sample_hop", "rank_kernel", "relabel_kernel",
                                                                   "batch_generate", "release_kernel", "seed_local"))}
 tot = sum(v[1] for v in step.values()) or 1.0
@@ -59,7 +59,17 @@ with open(f"profiles/{tag}_ncu_full_summary.md", "w") as f:
         t = (float(gather["dram__bytes_read.sum"]) + float(gather["dram__bytes_write.sum"])) * 1e6
         f.write(f"\nGather (one fused launch per step): DRAM traffic {t / 1e6:.1f} MB per launch "
                 f"(read {gather['dram__bytes_read.sum']} MB + write {gather['dram__bytes_write.sum']} MB).\n")
-        json.dump({"traffic_bytes_per_step": t,
-                   "source": f"profiles/{tag}_ncu_full_summary.md: dram__bytes_read.sum+dram__bytes_write.sum of the fused gather launch of one step (ncu --set full)"},
-                  open("profiles/roofline_traffic.json", "w"))
+        # keyed by workload / D / Kg; per-row bytes let bench.py scale the figure to the rows of its own launch
+        try:
+            table = json.load(open("profiles/roofline_traffic.json"))
+        except Exception:
+            table = {}
+        if bench:
+            j = json.loads([l for l in open(bench) if l.startswith("{")][-1])
+            rows = j["roofline"]["rows_per_step"]
+            key = j["roofline"]["traffic_key"]
+            table[key] = {"bytes_per_launch": t, "rows_per_launch": rows, "bytes_per_row": t / rows,
+                          "source": f"profiles/{tag}_ncu_full_summary.md: dram__bytes_read.sum+dram__bytes_write.sum of the fused gather launch "
+                                    f"(ncu --set full, `{cmd}`): {t / rows:.1f} B per gathered row"}
+            json.dump(table, open("profiles/roofline_traffic.json", "w"), indent=1)
 print("ok")
