@@ -197,8 +197,7 @@ class HostCSR:
             os.unlink(base + ".indptr")
             os.unlink(base + ".indices")
         self._copy(ip, self.indptr, (N + 1) * rank // world, (N + 1) * (rank + 1) // world)
-        self._copy(ix, self.indices, E * rank // world, E * (rank + 1) // world)
-        torch.cuda.synchronize()
+        self._copy(ix, self.indices, E * rank // world, E * (rank + 1) // world)  # .cpu() copies are synchronous
         dist.barrier()
 
     @staticmethod
@@ -896,7 +895,7 @@ def cpu_arm(shape, indptr, indices, train, steps, warmup):
         O.synth_features(r0, min(1 << 24, n_feat - r0), D, SEED, out=feat[r0:r0 + (1 << 24)])
     log(f"[cpu arm] feature matrix {n_feat} x {D} on the host in {time.time() - t0:.1f}s ({base.threads()} threads)")
     out = np.empty((O.num_ids(B, fanout), D), np.float32)
-    n_batches = (len(train) - 1) // B
+    n_batches = max(1, (len(train) - 1) // B)
     times, rows = [], 0
     for s in range(warmup + steps):
         seeds = train[(s % n_batches) * B:(s % n_batches + 1) * B]

@@ -81,3 +81,32 @@ def test_clique_arithmetic():
     assert multigpu.clique_of(5, 4) == (1, 1, 4)
     assert multigpu.clique_of(7, 8) == (0, 7, 0)
     assert multigpu.clique_of(2, 1) == (2, 0, 2)
+
+
+def _csr_worker(rank, world, port, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from legion_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    indptr, indices = synth.graph(3000, 6.0, 200, 11)  # every rank holds the identical graph (as it does in HBM)
+    csr = bench.HostCSR(torch.from_numpy(indptr), torch.from_numpy(indices), 3000, len(indices), rank, world, dist)
+    leftovers = [f for f in os.listdir("/dev/shm") if f.startswith("legion_b200_csr_")]
+    out[rank] = dict(ok=bool(np.array_equal(csr.indptr, indptr) and np.array_equal(csr.indices, indices)),
+                     shared=isinstance(csr.indptr, np.memmap), leftovers=leftovers)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_csr_is_shared_once_per_box():
+    """bench.py's parity self-check (N > 1): one host copy of the CSR in /dev/shm, each rank writes its slice, every rank
+    sees the whole graph, and the names are unlinked as soon as everybody has them mapped"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_csr_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        assert out[r]["ok"] and out[r]["shared"] and out[r]["leftovers"] == [], out[r]
