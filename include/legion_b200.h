@@ -202,6 +202,12 @@ int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, const lg_fe
 /* IOSubmit is a no-op in the reference (engine/operator_impl.cu:521-539); kept for API parity. */
 int lg_io_submit(lg_sampler* s, lg_stream_t stream, int32_t op_id, const lg_batch* batch);
 
+/* Copies the used part of one set of batch buffers into another: ids[0, nc[9+H]), labels[0, nc[9]), agg_src / agg_dst
+ * [0, ec[9+H]) and both counter arrays; the sizes are read from `from`'s counters on the device (one launch, no host
+ * synchronisation).  For hosts that sample into private staging buffers while the consumer still owns the hand-off
+ * buffers (the reference samples straight into them and therefore waits, engine/server.cu:309). */
+int lg_batch_publish(lg_stream_t stream, const lg_batch* from, const lg_batch* to);
+
 /* IOComplete (engine/operator_impl.cu:542-580): end-of-batch cleanup (ClearPosMap: the position-map words
  * of the batch's vertices are released, in every mode) and, in train mode when node_hotness != NULL, HotnessMeasure
  * (cache/cache_impl.cuh:190-198) plus the running max of unique ids (cache/cache.cu:59-61,

@@ -72,6 +72,7 @@ _PROTOS = {
     "lg_feature_cache_lookup": (C.c_int, [vp, vp, C.POINTER(FeatureCache), C.c_int32, C.c_int32, C.POINTER(Batch), vp]),
     "lg_feature_cache_lookup_range": (C.c_int, [vp, vp, C.POINTER(FeatureCache), C.c_int32, C.c_int32, C.c_int32,
                                               C.POINTER(Batch), vp]),
+    "lg_batch_publish": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(Batch)]),
     "lg_io_submit": (C.c_int, [vp, vp, C.c_int32, C.POINTER(Batch)]),
     "lg_io_complete": (C.c_int, [vp, vp, C.c_int32, C.POINTER(Batch), vp, vp]),
     "lg_run_batch": (C.c_int, [vp, vp, C.POINTER(Topology), C.POINTER(FeatureCache), C.POINTER(BatchParams),

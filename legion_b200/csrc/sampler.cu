@@ -820,6 +820,33 @@ __global__ void __launch_bounds__(kBlock, 6) chain_kernel(const ChainArgs c) {
   relabel_body(c.smp.agg_src, c.rnk.ec, gtid, n_threads);
 }
 
+// lg_batch_publish: the used part of one buffer set copied into another (ids, labels, COO, counters), one launch
+struct PublishArgs {
+  const int32_t *ids, *labels, *agg_src, *agg_dst, *nc, *ec;
+  int32_t *o_ids, *o_labels, *o_agg_src, *o_agg_dst, *o_nc, *o_ec;
+};
+__global__ void __launch_bounds__(kBlock) publish_kernel(const PublishArgs a) {
+  pdl_prologue();
+  const int32_t hops = ld_counter(a.nc + LG_INTRABATCH_CON * 3 - 1);
+  const int32_t B = ld_counter(a.nc + LG_INTRABATCH_CON * 3);
+  const int32_t n = hops >= 0 && hops <= LG_MAX_HOPS ? ld_counter(a.nc + LG_INTRABATCH_CON * 3 + hops) : 0;
+  const int32_t e = hops >= 0 && hops <= LG_MAX_HOPS ? ld_counter(a.ec + LG_INTRABATCH_CON * 3 + hops) : 0;
+  const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x, nt = (int64_t)gridDim.x * kBlock;
+  auto copy = [&](const int32_t* __restrict__ src, int32_t* __restrict__ dst, int32_t count) {
+    const int32_t n4 = count >> 2;  // the buffers are cudaMalloc'ed: 16-byte aligned
+    for (int64_t i = t; i < n4; i += nt) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(src)[i];
+    for (int64_t i = (int64_t)n4 * 4 + t; i < count; i += nt) dst[i] = src[i];
+  };
+  copy(a.ids, a.o_ids, n);
+  copy(a.agg_src, a.o_agg_src, e);
+  copy(a.agg_dst, a.o_agg_dst, e);
+  copy(a.labels, a.o_labels, B);
+  if (t < LG_COUNTER_SLOTS) {
+    a.o_nc[t] = a.nc[t];
+    a.o_ec[t] = a.ec[t];
+  }
+}
+
 // HotnessMeasure (cache/cache_impl.cuh:190-198) + max_ids_ (cache/cache.cu:59-61)
 __global__ void __launch_bounds__(kBlock) hotness_measure_kernel(const int32_t* __restrict__ ids,
                                                                  const int32_t* __restrict__ nc, u64* node_hot,
@@ -1434,6 +1461,15 @@ extern "C" int lg_random_sample(lg_sampler* s, lg_stream_t stream_, const lg_top
 }
 
 extern "C" int lg_io_submit(lg_sampler*, lg_stream_t, int32_t, const lg_batch*) { return 0; }
+
+extern "C" int lg_batch_publish(lg_stream_t stream, const lg_batch* from, const lg_batch* to) {
+  LG_REQUIRE(from && to && from->ids && to->ids && from->node_counter && to->node_counter, "lg_batch_publish: null argument");
+  LG_REQUIRE(to->num_ids >= from->num_ids, "lg_batch_publish: destination holds %d ids, source %d", to->num_ids, from->num_ids);
+  PublishArgs a{from->ids, from->labels, from->agg_src, from->agg_dst, from->node_counter, from->edge_counter,
+                to->ids,   to->labels,   to->agg_src,   to->agg_dst,   to->node_counter,   to->edge_counter};
+  LG_CUDA(lg_launch_opt(lg_pdl() != 0, publish_kernel, kSMs * 4, kBlock, 0, (cudaStream_t)stream, a));
+  return 0;
+}
 
 extern "C" int lg_io_complete(lg_sampler* s, lg_stream_t stream_, int32_t mode, const lg_batch* b,
                               unsigned long long* node_hotness, int32_t* max_ids) {

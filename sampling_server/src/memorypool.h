@@ -17,11 +17,18 @@ class MemoryPool {
   int32_t GetCurrentPipe() const { return current_pipe_; }
   void SetGlobalBatchId(int32_t g) { global_batch_id_ = g; }
   int32_t GetGlobalBatchId() const { return global_batch_id_; }
-  lg_batch* Batch() { return &batch_[current_pipe_]; }
+  // the buffers the operators of the batch in flight work on: the IPC slot, or (staged sampling, server.cc) a
+  // server-private staging set while the trainer still owns the slot
+  lg_batch* Batch() { return view_ ? view_ : &batch_[current_pipe_]; }
   lg_batch* Batch(int pipe) { return &batch_[pipe]; }
+  void SetBatchView(lg_batch* v) { view_ = v; }
+  void SetCurrentSampler(int32_t i) { current_sampler_ = i; }
   // one sampler handle (position map, scan state, frontier scratch) per pipeline slot: the sampling of batch i+1
   // does not queue behind batch i's on a shared handle (the reference has one scratch set per GPU, engine/server.cu:221-234)
-  lg_sampler* Sampler() { return samplers[samplers.size() > 1 ? current_pipe_ : 0]; }
+  lg_sampler* Sampler() {
+    if (current_sampler_ >= 0 && current_sampler_ < (int32_t)samplers.size()) return samplers[current_sampler_];
+    return samplers[samplers.size() > 1 ? current_pipe_ : 0];
+  }
   lg_sampler* Sampler(int pipe) { return samplers[samplers.size() > 1 ? pipe : 0]; }
   std::vector<lg_sampler*> samplers;
   int32_t rng_kind = LG_RNG_PHILOX;
@@ -29,5 +36,6 @@ class MemoryPool {
 
  private:
   std::vector<lg_batch> batch_;
-  int32_t iter_ = 0, mode_ = 0, current_pipe_ = 0, global_batch_id_ = 0;
+  int32_t iter_ = 0, mode_ = 0, current_pipe_ = 0, global_batch_id_ = 0, current_sampler_ = -1;
+  lg_batch* view_ = nullptr;
 };

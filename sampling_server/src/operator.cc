@@ -30,7 +30,7 @@ class BatchGenerateOP : public Operator {
       ids = feature->GetTestingSetIds(dev); labels = feature->GetTestingLabels(dev); cap = feature->TestingSetSize(dev);
     }
     LGCHECK(lg_batch_generate(pool->Sampler(), params->stream, ids, labels, cap, batch_size, iter, pool->Batch()));
-    LGCHECK(lg_event_record(params->event, params->stream));
+    if (params->event) LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:
   int op_id_;
@@ -48,7 +48,7 @@ class RandomSampleOP : public Operator {
     unsigned long long* edge_hot = params->is_presc ? cache->GetEdgeAccessedMap(dev) : nullptr;
     LGCHECK(lg_random_sample(pool->Sampler(), params->stream, graph->Topology(dev), op_id_ / INTRABATCH_CON, pool->rng_kind,
                              pool->rng_seed, (uint32_t)pool->GetGlobalBatchId(), (uint32_t)dev, pool->Batch(), edge_hot));
-    LGCHECK(lg_event_record(params->event, params->stream));
+    if (params->event) LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:
   int op_id_;
@@ -76,7 +76,7 @@ class CacheLookupOP : public Operator {
     else if (last)
       LGCHECK(lg_feature_cache_lookup_range(pool->Sampler(), params->stream, cache->FeatureCache(dev), op_id_, 0,
                                             cache->LocalPart(dev), pool->Batch(), cache->TierRows(dev)));
-    LGCHECK(lg_event_record(params->event, params->stream));
+    if (params->event) LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:
   int op_id_;
@@ -88,7 +88,7 @@ class SSDIOSubmitOP : public Operator {
   void run(OpParams* params) override {
     auto* pool = (MemoryPool*)params->memorypool;
     LGCHECK(lg_io_submit(pool->Sampler(), params->stream, op_id_, pool->Batch()));
-    LGCHECK(lg_event_record(params->event, params->stream));
+    if (params->event) LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:
   int op_id_;
@@ -104,7 +104,7 @@ class SSDIOCompleteOP : public Operator {
     bool presc = params->is_presc;
     LGCHECK(lg_io_complete(pool->Sampler(), params->stream, pool->GetCurrentMode(), pool->Batch(),
                            presc ? cache->GetNodeAccessedMap(dev) : nullptr, presc ? cache->MaxIdsDevice(dev) : nullptr));
-    LGCHECK(lg_event_record(params->event, params->stream));
+    if (params->event) LGCHECK(lg_event_record(params->event, params->stream));
   }
  private:
   int op_id_;

@@ -172,7 +172,13 @@ class GPURunner : public Runner {
     int max_batch = batch_size;
     for (int m : {VALIDMODE, TESTMODE})
       if (env->GetCurrentBatchsize(local_dev_id_, m) > max_batch) max_batch = env->GetCurrentBatchsize(local_dev_id_, m);
-    memorypool_->samplers.assign(slot_samplers_ ? interbatch_concurrency_ : 1, nullptr);
+    {  // staged sampling (RunOnceStaged): LEGION_STAGING=k sampling stages (default 3; 0 = sample straight into the IPC slot)
+      const char* e = std::getenv("LEGION_STAGING");
+      n_stage_ = e ? std::atoi(e) : 3;
+      if (!slot_samplers_ || n_stage_ < 2) n_stage_ = 0;
+      if (n_stage_ > 4) n_stage_ = 4;
+    }
+    memorypool_->samplers.assign(n_stage_ ? n_stage_ : (slot_samplers_ ? interbatch_concurrency_ : 1), nullptr);
     if (max_batch > batch_size) num_ids_ = (int32_t)lg_num_ids(max_batch, params->fanout.data(), hop_num);
     if (const char* e = std::getenv("LEGION_RNG")) memorypool_->rng_kind = std::strcmp(e, "minstd") == 0 ? LG_RNG_MINSTD : LG_RNG_PHILOX;
     if (const char* e = std::getenv("LEGION_SEED")) memorypool_->rng_seed = std::strtoull(e, nullptr, 0);
@@ -220,6 +226,32 @@ class GPURunner : public Runner {
       }
     }
     current_pipe_ = 0;
+    stage_b_.resize(n_stage_);
+    stage_stream_.resize(n_stage_);
+    sampled_ev_.resize(n_stage_);
+    copied_ev_.resize(n_stage_);
+    for (int i = 0; i < n_stage_; i++) {  // server-private twins of the slot's small buffers (everything but the features)
+      lg_batch& b = stage_b_[i];
+      std::memset(&b, 0, sizeof(b));
+      auto alloc = [&](int64_t words) {
+        void* p = nullptr;
+        LGCHECK(lg_device_alloc(&p, words * 4));
+        LGCHECK(lg_memset_async(p, 0, words * 4, nullptr));
+        return (int32_t*)p;
+      };
+      b.ids = alloc(num_ids_);
+      b.labels = alloc(max_batch);
+      b.agg_src = alloc(num_ids_);
+      b.agg_dst = alloc(num_ids_);
+      b.node_counter = alloc(LG_COUNTER_SLOTS);
+      b.edge_counter = alloc(LG_COUNTER_SLOTS);
+      b.num_ids = num_ids_;
+      b.feature_rows = 0;
+      LGCHECK(lg_stream_create(&stage_stream_[i]));
+      LGCHECK(lg_event_create(&sampled_ev_[i]));
+      LGCHECK(lg_event_create(&copied_ev_[i]));
+    }
+
     for (int i = 0; i < interbatch_concurrency_; i++) {
       lg_batch* b = memorypool_->Batch(i);
       std::memset(b, 0, sizeof(*b));
@@ -300,8 +332,103 @@ class GPURunner : public Runner {
   // RunOnce(i) launches batch i and then completes batch i-1 (host-level software pipeline over the
   // INTERBATCH_CON slots): the gather tail of batch i-1 (stream 1) overlaps the sampling of batch i
   // (stream 0).  The trainer still sees batches strictly in order, one semaphore post per batch.
+  // ---- staged sampling: three batches in flight over the wire's two slots ----
+  // The trainer owns a slot until it calls synchronize(); the reference (and RunOnce below) can therefore only have two
+  // batches in flight.  But only the GATHER needs the slot's feature buffer: the sampling chain of batch g runs into a
+  // server-private staging set (ids, labels, COO, counters: 27 MB) without waiting for anybody; when the slot of batch g-1
+  // is free, one copy kernel (lg_batch_publish) publishes its staging set into the slot and the gather, the CSC builder and the
+  // counter / status copies follow on the slot's streams; batch g-2 is handed over.  Per iteration:
+  //   A(g)   sample batch g into stage g % S                       (stream of the stage, sampler of the stage)
+  //   B(g-1) IPCWait(slot); stage -> slot copies; lookup ops, ...  (streams of the slot)
+  //   C(g-2) join, IPCPost
+  // The trainer sees the same buffers, the same counters and the same order.  LEGION_STAGING=0 disables it.
+  void StageA(IPCEnv* env, int32_t g) {
+    const int s = g % n_stage_;
+    memorypool_->SetCurrentMode(env->GetCurrentMode(g));
+    memorypool_->SetIter(env->GetLocalBatchId(g));
+    memorypool_->SetGlobalBatchId(g);
+    memorypool_->SetCurrentSampler(s);
+    memorypool_->SetBatchView(&stage_b_[s]);
+    lg_stream_t st = stage_stream_[s];
+    LGCHECK(lg_stream_wait_event(st, copied_ev_[s]));  // the stage's previous batch has been published (no-op the first time)
+    for (int i = 0; i < op_num_; i += INTRABATCH_CON) {  // ops 0, 3, 6, ..: batch_generate, the sampling ops, io_complete
+      op_params_[i]->is_presc = false;
+      op_params_[i]->stream = st;
+      op_params_[i]->event = nullptr;  // nothing waits for a single op of the chain: no event between its kernels, so
+                                       // they stay chained by programmatic dependent launch; the stage's event follows
+      ops_[i]->run(op_params_[i]);
+    }
+    LGCHECK(lg_event_record(sampled_ev_[s], st));
+    memorypool_->SetBatchView(nullptr);
+  }
+  void StageB(IPCEnv* env, int32_t g) {
+    const int s = g % n_stage_, pipe = g % interbatch_concurrency_;
+    env->IPCWait(local_dev_id_, pipe);
+    memorypool_->SetCurrentPipe(pipe);
+    memorypool_->SetCurrentSampler(s);
+    memorypool_->SetBatchView(nullptr);
+    auto& st = streams_[pipe];
+    auto& ev = events_[pipe];
+    const lg_batch& from = stage_b_[s];
+    lg_batch* to = memorypool_->Batch(pipe);
+    LGCHECK(lg_stream_wait_event(st[0], sampled_ev_[s]));
+    LGCHECK(lg_batch_publish(st[0], &from, to));  // the used part of ids / labels / COO / counters, one launch
+    LGCHECK(lg_event_record(copied_ev_[s], st[0]));
+    for (int i = 0; i < op_num_; i += INTRABATCH_CON) LGCHECK(lg_event_record(ev[i], st[0]));  // "the sampling op of the hop is done"
+    for (int i = 0; i < op_num_; i++) {
+      if (i % INTRABATCH_CON == 0) continue;  // ran in stage A
+      LGCHECK(lg_stream_wait_event(st[i % INTRABATCH_CON], ev[i / INTRABATCH_CON * INTRABATCH_CON]));
+      op_params_[i]->is_presc = false;
+      op_params_[i]->stream = st[i % INTRABATCH_CON];
+      op_params_[i]->event = ev[i];
+      ops_[i]->run(op_params_[i]);
+    }
+    AfterOps(env, pipe);
+  }
+  void RunOnceStaged(RunnerParams* params) {
+    auto* env = (IPCEnv*)params->env;
+    const int32_t g = params->global_batch_id, last = env->GetMaxStep() - 1;
+    StageA(env, g);
+    if (g >= 1) StageB(env, g - 1);
+    if (g >= 2) Complete(env, (g - 2) % interbatch_concurrency_, g - 2);
+    if (g == last) {  // drain
+      StageB(env, g);
+      if (g >= 1) Complete(env, (g - 1) % interbatch_concurrency_, g - 1);
+      Complete(env, g % interbatch_concurrency_, g);
+    }
+    current_pipe_ = (g + 1) % interbatch_concurrency_;
+    memorypool_->SetCurrentSampler(-1);
+  }
+
+  // what follows a batch's ops on the slot's streams: blocks as CSC, counters to the host side channel, status
+  void AfterOps(IPCEnv* env, int pipe) {
+    auto& ev = events_[pipe];
+    auto& st = streams_[slot_samplers_ ? pipe : 0];
+    if (emit_csc_) {  // the third stream is idle in the reference (SSDIOSubmit is a no-op): the blocks are built there, behind
+                      // the last sampling op, while the gather streams on the second
+      LGCHECK(lg_stream_wait_event(st[2], ev[op_num_ - 1 - INTRABATCH_CON]));
+      const int hops = (int)csc_max_edges_.size();
+      int32_t** ptrs = &csc_ptrs_[(size_t)pipe * 3 * hops];  // [indptr | indices | eids][block]
+      LGCHECK(lg_block_csc_batch(st[2], memorypool_->Batch(pipe), hops, csc_max_edges_.data(), csc_max_dst32_.data(),
+                                 ptrs, ptrs + hops, ptrs + 2 * hops, csc_workspace_[pipe], csc_workspace_bytes_));
+      LGCHECK(lg_event_record(csc_ev_[pipe], st[2]));
+    }
+    // the side channel (include/legion_b200_ext.h): the batch's counters go to host memory behind its last lookup (which
+    // waited for the last sampling op), so that the trainer's get_next needs no device copy of its own
+    if (int32_t* hc = env->GetHostCounters(local_dev_id_, pipe)) {
+      const lg_batch* b = memorypool_->Batch(pipe);
+      LGCHECK(lg_memcpy_d2h(hc, b->node_counter, LG_COUNTER_SLOTS * sizeof(int32_t), st[1]));
+      LGCHECK(lg_memcpy_d2h(hc + LG_COUNTER_SLOTS, b->edge_counter, LG_COUNTER_SLOTS * sizeof(int32_t), st[1]));
+    }
+    // the sticky overflow flag as of this batch's last lookup: an asynchronous copy behind it (a synchronous read on any
+    // of the three streams would wait for the batch just launched, not for the one being handed off)
+    LGCHECK(lg_sampler_status_async(memorypool_->Sampler(), st[1], status_host_[pipe]));
+    LGCHECK(lg_event_record(status_ev_[pipe], st[1]));
+  }
+
   void RunOnce(RunnerParams* params) override {
     LGCHECK(lg_set_device(local_dev_id_));
+    if (n_stage_ > 0) return RunOnceStaged(params);
     auto* env = (IPCEnv*)params->env;
     int32_t batch_id = params->global_batch_id;
     mode_ = env->GetCurrentMode(batch_id);
@@ -320,26 +447,7 @@ class GPURunner : public Runner {
       op_params_[i]->event = ev[i];
       ops_[i]->run(op_params_[i]);
     }
-    if (emit_csc_) {  // the third stream is idle in the reference (SSDIOSubmit is a no-op): the blocks are built there, behind
-                      // the last sampling op, while the gather streams on the second
-      LGCHECK(lg_stream_wait_event(st[2], ev[op_num_ - 1 - INTRABATCH_CON]));
-      const int hops = (int)csc_max_edges_.size();
-      int32_t** ptrs = &csc_ptrs_[(size_t)current_pipe_ * 3 * hops];  // [indptr | indices | eids][block]
-      LGCHECK(lg_block_csc_batch(st[2], memorypool_->Batch(current_pipe_), hops, csc_max_edges_.data(), csc_max_dst32_.data(),
-                                 ptrs, ptrs + hops, ptrs + 2 * hops, csc_workspace_[current_pipe_], csc_workspace_bytes_));
-      LGCHECK(lg_event_record(csc_ev_[current_pipe_], st[2]));
-    }
-    // the side channel (include/legion_b200_ext.h): the batch's counters go to host memory behind its last lookup (which
-    // waited for the last sampling op), so that the trainer's get_next needs no device copy of its own
-    if (int32_t* hc = env->GetHostCounters(local_dev_id_, current_pipe_)) {
-      const lg_batch* b = memorypool_->Batch(current_pipe_);
-      LGCHECK(lg_memcpy_d2h(hc, b->node_counter, LG_COUNTER_SLOTS * sizeof(int32_t), st[1]));
-      LGCHECK(lg_memcpy_d2h(hc + LG_COUNTER_SLOTS, b->edge_counter, LG_COUNTER_SLOTS * sizeof(int32_t), st[1]));
-    }
-    // the sticky overflow flag as of this batch's last lookup: an asynchronous copy behind it (a synchronous read on any
-    // of the three streams would wait for the batch just launched, not for the one being handed off)
-    LGCHECK(lg_sampler_status_async(memorypool_->Sampler(), st[1], status_host_[current_pipe_]));
-    LGCHECK(lg_event_record(status_ev_[current_pipe_], st[1]));
+    AfterOps(env, current_pipe_);
     if (pending_pipe_ >= 0) Complete(env, pending_pipe_, pending_batch_);
     pending_pipe_ = current_pipe_;
     pending_batch_ = batch_id;
@@ -387,6 +495,10 @@ class GPURunner : public Runner {
   int current_pipe_ = 0, interbatch_concurrency_ = INTERBATCH_CON, local_dev_id_ = 0, mode_ = 0, op_num_ = 0;
   bool slot_samplers_ = true;
   bool emit_csc_ = false;
+  int n_stage_ = 0;  // staged sampling: number of staging sets (0 = off)
+  std::vector<lg_batch> stage_b_;
+  std::vector<lg_stream_t> stage_stream_;
+  std::vector<lg_event_t> sampled_ev_, copied_ev_;
   std::vector<int64_t> csc_max_edges_, csc_max_dst_;
   std::vector<int32_t> csc_max_dst32_;
   std::vector<int32_t*> csc_ptrs_;  // [slot][indptr | indices | eids][block]
