@@ -34,6 +34,8 @@ struct GatherArgs {
   int32_t l2;          // lg_l2_hints()
   int32_t* ticket;     // [2] zeroed: tiles are claimed dynamically (robust to CTAs that start late or run slowed down next to
                        // another kernel); null = static round-robin over the grid
+  int32_t chunk;       // consecutive tiles per chunk (static order) / per claim (dynamic)
+  int32_t static_pct;  // dynamic: share of a CTA's fair share that keeps the static order (no atomics)
 };
 
 __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int64_t* cnt) {
@@ -157,6 +159,16 @@ __global__ void __launch_bounds__(256) gather_ldg_kernel(const GatherArgs a) {
 }
 
 // ---------------- TMA mover: bulk async copies through shared memory ----------------
+// The tile counter's atomicAdd as inline PTX: written as `if (lane == 0) c = atomicAdd(...)`, nvcc placed the broadcast of
+// the result (SHFL) directly behind the ATOMG — ptxas aggregates an `atom.add` over the active lanes (VOTE / POPC / elected
+// ATOMG / SHFL of the result), also for inline PTX, so the warp waited for every claim's round trip although the value is
+// only needed a whole chunk later.  `atom.inc` (wrap bound 2^31-1: a plain increment here) is not aggregated: the result
+// stays in lane 0's register until claim() reads it.
+__device__ __forceinline__ int32_t atom_inc_deferred(int32_t* p) {
+  uint32_t old;
+  asm volatile("atom.relaxed.gpu.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "l"(p) : "memory");
+  return (int32_t)old;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -202,7 +214,7 @@ __device__ __forceinline__ void bulk_wait_read() {
 // Pipeline: iteration `it` fills stage it % STAGES with tile(it) and drains tile(it - LAG),
 // LAG = STAGES - 2: LAG tiles of row loads in flight, one stage being stored, one being refilled.
 template <int STAGES, int kTmaRows>
-__global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
+__global__ void __maxnreg__(40) gather_tma_kernel(const GatherArgs a) {
   static_assert(STAGES >= 3, "need a stage in store and a stage in refill besides the loads in flight");
   constexpr int LAG = STAGES - 2;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -223,28 +235,48 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   }
   __syncwarp();
   int32_t t0 = 0, t1 = 0, t2 = 0;
-  __shared__ int64_t s_tileidx[STAGES];
+  __shared__ int s_tileidx[STAGES];
 
-  // Tile order.  Static: tile(it) = blockIdx.x + it * gridDim.x.  Dynamic (a.ticket): tiles are claimed from a global
-  // counter, two iterations ahead of their row loads — a CTA that starts late (its SM still busy with another
-  // kernel's CTAs) or whose warp gets fewer issue slots simply ends up moving fewer tiles, instead of holding the
-  // whole launch back with a fixed share.  Claims are monotone: once one fails, every later one fails too.
-  auto claim = [&](int64_t it) -> int64_t {
-    int64_t t;
-    if (a.ticket) {
-      int32_t c = 0;
-      if (lane == 0) c = atomicAdd(a.ticket, 1);
-      t = __shfl_sync(0xffffffffu, c, 0);
-    } else {
-      t = blockIdx.x + it * (int64_t)gridDim.x;
+  // Tile order.  A CTA works on chunks of a.chunk consecutive tiles (consecutive ids, consecutive destination rows).
+  // Static: chunk k of CTA b is b + k * gridDim.x.  Dynamic (a.ticket): a CTA's first chunk is its block index, every later
+  // one comes from a global counter
+  // whose atomicAdd is issued a whole chunk BEFORE its result is needed (the first version claimed every tile with a
+  // returning atomic and waited for it: half the bandwidth) — a CTA that starts late (its SM still busy with another
+  // kernel's CTAs) or whose warp gets fewer issue slots simply ends up moving fewer tiles instead of holding the whole
+  // launch back with a fixed share.  Claims are monotone: once one fails, every later one would fail too.
+  // (tile indices are 32-bit: a launch moves fewer than 2^31 ROWS, checked by the host)
+  const int nt = (int)n_tiles, grid = (int)gridDim.x;
+  int chunk = a.chunk > 0 ? a.chunk : 1;
+  if (chunk > nt / grid) chunk = nt / grid > 0 ? nt / grid : 1;  // few tiles: every CTA gets some
+  // dynamic: the first k_static rounds of chunks (a.static_pct % of a CTA's fair share) keep the static order and cost
+  // no atomics; only the rest of the launch is handed out by the counter
+  int k_static = 1;
+  if (a.ticket && a.static_pct > 0) k_static = (int)((int64_t)((nt + chunk - 1) / chunk / grid) * a.static_pct / 100);
+  if (k_static < 1) k_static = 1;
+  int static_left = a.ticket ? k_static - 1 : 0x7fffffff;
+  int ch_index = blockIdx.x;  // index of the chunk being worked on (static order) / base of the counter's chunks (dynamic)
+  int ch_next = 0;            // next tile of the chunk being worked on, relative to it
+  int32_t ch_pending = 0;     // dynamic, lane 0: the counter value of the chunk after this one (in flight until it is used)
+  if (a.ticket && static_left == 0 && lane == 0) ch_pending = atom_inc_deferred(a.ticket);
+  auto claim = [&]() -> int {
+    if (ch_next == chunk) {
+      ch_next = 0;
+      if (static_left > 0) {
+        ch_index += grid;
+        if (--static_left == 0 && lane == 0) ch_pending = atom_inc_deferred(a.ticket);  // (never reached without a counter)
+      } else {
+        ch_index = k_static * grid + __shfl_sync(0xffffffffu, ch_pending, 0);
+        if (lane == 0 && ch_index * chunk < nt) ch_pending = atom_inc_deferred(a.ticket);
+      }
     }
-    return t < n_tiles ? t : -1;
+    const int t = ch_index * chunk + ch_next++;
+    return t < nt ? t : -1;
   };
 
   // The id -> directory -> pointer chain is software-pipelined so that no iteration waits on it:
   // ids are loaded two tiles ahead, directory entries one tile ahead, pointers are formed at use.
-  auto load_id = [&](int64_t tile) -> int32_t {
-    const int64_t r = tile * kTmaRows + lane;
+  auto load_id = [&](int tile) -> int32_t {
+    const int64_t r = (int64_t)tile * kTmaRows + lane;
     if (tile < 0 || lane >= kTmaRows || r >= cnt) return -1;
     if (off + r >= a.dst_rows) {
       *a.status = 2;
@@ -277,13 +309,13 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
     if (didx == a.local_part) t0++; else t1++;
     return a.cache.shard[didx] + (int64_t)fidx * a.cache.dim;
   };
-  int64_t tile0 = claim(0);
-  int64_t tile1 = tile0 >= 0 ? claim(1) : -1;
+  int tile0 = claim();
+  int tile1 = tile0 >= 0 ? claim() : -1;
   int32_t id0 = load_id(tile0), id1 = load_id(tile1);
   int32_t loc0 = load_loc(id0);
-  int64_t n_issued = 0;  // tiles whose loads this CTA issued; the drain runs LAG iterations behind
-  for (int64_t it = 0; tile0 >= 0 || it < n_issued + LAG; it++) {
-    const int64_t tile2 = tile1 >= 0 ? claim(it + 2) : -1;
+  int n_issued = 0;  // tiles whose loads this CTA issued; the drain runs LAG iterations behind
+  for (int it = 0; tile0 >= 0 || it < n_issued + LAG; it++) {
+    const int tile2 = tile1 >= 0 ? claim() : -1;
     const int32_t id2 = load_id(tile2);
     const int32_t loc1 = load_loc(id1);
     const float* src = form_ptr(id0, loc0);
@@ -309,7 +341,7 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
     id0 = id1;
     id1 = id2;
     loc0 = loc1;
-    const int64_t dt = it - LAG;
+    const int dt = it - LAG;
     if (dt >= 0 && dt < n_issued) {
       const int s = (int)(dt % STAGES);
       const uint32_t parity = (uint32_t)((dt / STAGES) & 1);
@@ -335,7 +367,9 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tier_flush(a, t0, t1, t2, lane);
   if (a.ticket && lane == 0) {  // the last CTA out re-arms the counters for the next launch on this stream
+    __threadfence();  // this CTA's claims (also the one it never looked at) are performed before it counts as done
     if (atomicAdd(a.ticket + 1, 1) == (int32_t)gridDim.x - 1) {
+      __threadfence();
       a.ticket[0] = 0;
       a.ticket[1] = 0;
     }
@@ -351,11 +385,11 @@ __global__ void __launch_bounds__(32) gather_tma_kernel(const GatherArgs a) {
 // co-resident.  8-row tiles on 10-12 single-warp CTAs keep as many bytes in flight with 130 KB (alone: 0.81 of the HBM peak
 // instead of 0.85 at D=128, unchanged at D=100) and leave 124 KB of L1: UK-Union shape 16.4 -> 18.9 M seeds/s.
 struct Tune {
-  int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows, carveout, smem_kb;
+  int ldg_r, tma_stages, ldg_ctas, tma_ctas, tma_rows, carveout, smem_kb, chunk;
 };
 static const Tune& tune() {
   static Tune t = [] {
-    Tune x{8, 3, 8, 8, 8, -1, 130};  // LDG: R=8 rows per warp (profiles/r01_gather_sweep_v3.txt)
+    Tune x{8, 3, 8, 8, 8, -1, 130, 1};  // LDG: R=8 rows per warp (profiles/r01_gather_sweep_v3.txt)
     if (const char* e = getenv("LG_LDG_R")) x.ldg_r = atoi(e);
     if (const char* e = getenv("LG_TMA_STAGES")) x.tma_stages = atoi(e);
     if (const char* e = getenv("LG_LDG_CTAS")) x.ldg_ctas = atoi(e);
@@ -363,6 +397,7 @@ static const Tune& tune() {
     if (const char* e = getenv("LG_TMA_ROWS")) x.tma_rows = atoi(e);
     if (const char* e = getenv("LG_GATHER_SMEM_KB")) x.smem_kb = atoi(e);
     if (const char* e = getenv("LG_GATHER_CARVEOUT")) x.carveout = atoi(e);
+    if (const char* e = getenv("LG_GATHER_CHUNK")) x.chunk = atoi(e) > 0 ? atoi(e) : 1;  // tiles per chunk, static order
     return x;
   }();
   return t;
@@ -417,6 +452,7 @@ int launch_ldg(cudaStream_t st, const GatherArgs& a, int64_t max_rows, bool vec_
 
 int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) {
   const int dim = a.cache.dim;
+  LG_REQUIRE(max_rows < (1ll << 31), "gather: %lld rows in one launch (tile indices are 32-bit)", (long long)max_rows);
   const bool vec_ok = (dim % 4 == 0) && (((uintptr_t)a.dst & 15) == 0) && (((uintptr_t)a.cache.backing & 15) == 0);
   const Tune& t = tune();
   if (variant == LG_GATHER_AUTO) variant = LG_GATHER_TMA;  // falls through to LDG when rows are not 16-byte multiples
@@ -482,6 +518,8 @@ extern "C" int lg_feature_cache_lookup_range(lg_sampler* s, lg_stream_t stream, 
   a.status = s->status;
   a.l2 = lg_l2_hints();
   a.ticket = s->gather_ticket;
+  a.chunk = s->gather_ticket ? s->gather_chunk : tune().chunk;
+  a.static_pct = s->gather_static_pct;
   LG_REQUIRE(a.hop <= s->n_hops, "lg_feature_cache_lookup: op_id %d beyond %d hops", op_id, s->n_hops);
   int64_t max_rows = 0;
   for (int h = first_hop; h <= a.hop; h++) max_rows += s->slots_per_hop[h];
@@ -520,5 +558,7 @@ extern "C" int lg_gather_rows(lg_stream_t stream, const lg_feature_cache* cache,
   a.status = dummy_status;
   a.l2 = lg_l2_hints();
   a.ticket = nullptr;  // no handle to own a counter: static tile order
+  a.chunk = tune().chunk;
+  a.static_pct = 0;
   return launch_gather((cudaStream_t)stream, a, variant, n);
 }

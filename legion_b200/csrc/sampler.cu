@@ -1071,7 +1071,11 @@ static int sampler_init(lg_sampler* s, int32_t device, int32_t max_batch, const 
   if (s->hashed) LG_CUDA(cudaMalloc(&s->seed_local, (size_t)max_batch * sizeof(int32_t)));
   {
     const char* e = getenv("LG_GATHER_DYNAMIC");
-    if (e && atoi(e) != 0) {  // opt-in: measured neutral to slightly negative (profiles/r01b_overlap.md)
+    s->gather_chunk = 4;
+    s->gather_static_pct = 0;
+    if (const char* p = getenv("LG_GATHER_STATIC_PCT")) s->gather_static_pct = atoi(p) < 0 ? 0 : (atoi(p) > 100 ? 100 : atoi(p));
+    if (e && atoi(e) != 0) {  // opt-in; LG_GATHER_DYNAMIC = tiles per claim (1 = one claim per tile)
+      s->gather_chunk = atoi(e) > 0 ? atoi(e) : 4;
       LG_CUDA(cudaMalloc(&s->gather_ticket, 2 * sizeof(int32_t)));
       LG_CUDA(cudaMemset(s->gather_ticket, 0, 2 * sizeof(int32_t)));
     }

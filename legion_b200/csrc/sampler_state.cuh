@@ -48,6 +48,8 @@ struct lg_sampler {
   int32_t* status;       // device int32: 1 = ids overflow, 2 = features buffer overflow, 3 = miss without a backing matrix,
                          // 4 = edge_dst holds an id outside [0, num_nodes)
   int32_t* gather_ticket;  // [2] dynamic tile claims of the gather (re-armed by the kernel itself)
+  int32_t gather_chunk;    // tiles per claim
+  int32_t gather_static_pct;  // share of the launch that keeps the static tile order before the counter takes over
   int32_t* pinned_seeds;
   // gather/sampling overlap inside lg_run_batch: the gather of hop h runs on `side` while hop h+1
   // is sampled on the caller's stream (the reference's stream-1 / stream-0 split, server.cu:311-317)

@@ -433,3 +433,29 @@ def test_lazy_relabel_op_by_op(oracle, fanout, batch):
         torch.cuda.synchronize()
         assert_batch_equal(buf.to_host(H), want, H, feat)
     assert dp.status() == 0
+
+
+@pytest.mark.parametrize("chunk", [1, 4])
+def test_dynamic_gather_tiles(oracle, monkeypatch, chunk):
+    """LG_GATHER_DYNAMIC: the gather's CTAs claim chunks of tiles from a counter (prefetched one chunk ahead) instead of a
+    fixed share; more tiles than first chunks, several launches on one handle (the last CTA re-arms the counter)"""
+    monkeypatch.setenv("LG_GATHER_DYNAMIC", str(chunk))
+    indptr, indices = small_graph(200000, 10.0, 300, seed=11)
+    N = len(indptr) - 1
+    feat = _feat(N, 128)  # 512-byte rows: 10 single-warp CTAs per SM, 1480 first chunks
+    ids, labels = make_sets(N, frac=0.2)
+    fanout, B = [25, 10], 4096
+    rig = Rig(indptr, indices, feat, fanout, B)
+    rig.dp.set_gather_variant(capi.GATHER_TMA)
+    d_ids, d_lab = rig.sets(ids, labels)
+    buf = rig.dp.alloc_batch()
+    orc = oracle.Oracle(indptr, indices, fanout, B)
+    for counter in range(3):
+        p = rig.dp.params(d_ids, d_lab, B, counter, seed=99, batch_id=counter)
+        rig.dp.run_once(p, buf)
+        torch.cuda.synchronize()
+        want = orc.run_batch(ids, labels, B, counter, seed=99, batch_id=counter)
+        if counter == 0:
+            assert want["total_nodes"] > 1.5 * 148 * 10 * 8 * chunk  # later chunks come from the counter
+        assert_batch_equal(buf.to_host(2), want, 2, feat)
+    assert rig.dp.status() == 0
