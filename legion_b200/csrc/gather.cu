@@ -11,6 +11,8 @@
 //          mbarrier complete_tx), lane 0 drains a finished stage with ONE bulk store of the
 //          32 contiguous destination rows.  No registers touch the payload (SASS: UBLKCP).
 // Values are moved bit-for-bit (no arithmetic), so the output is bit-exact by construction.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "sampler_state.cuh"
 
@@ -36,6 +38,8 @@ struct GatherArgs {
                        // another kernel); null = static round-robin over the grid
   int32_t chunk;       // consecutive tiles per chunk (static order) / per claim (dynamic)
   int32_t static_pct;  // dynamic: share of a CTA's fair share that keeps the static order (no atomics)
+  int32_t use_g4;      // TMA mover: groups of 4 rows that all live in the local shard move as ONE tile::gather4 tensor copy
+  alignas(64) CUtensorMap tmap;  // 2-D view of shard[local_part] ([rows][dim] fp32, box = one row) for those copies
 };
 
 __device__ __forceinline__ void row_range(const GatherArgs& a, int64_t* off, int64_t* cnt) {
@@ -194,6 +198,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar), "l"(pol)
                : "memory");
 }
+// four rows of the 2-D table behind `tmap`, picked by row index, land back to back in shared memory (sm_100 TMA gather mode)
+__device__ __forceinline__ void tensor_gather4(uint32_t dst_smem, const CUtensorMap* tmap, int32_t r0, int32_t r1, int32_t r2,
+                                               int32_t r3, uint32_t bar, u64 pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;" ::"r"(dst_smem),
+      "l"(tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, u64 pol) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes),
                "l"(pol)
@@ -214,7 +227,7 @@ __device__ __forceinline__ void bulk_wait_read() {
 // Pipeline: iteration `it` fills stage it % STAGES with tile(it) and drains tile(it - LAG),
 // LAG = STAGES - 2: LAG tiles of row loads in flight, one stage being stored, one being refilled.
 template <int STAGES, int kTmaRows>
-__global__ void __maxnreg__(40) gather_tma_kernel(const GatherArgs a) {
+__global__ void __maxnreg__(40) gather_tma_kernel(const __grid_constant__ GatherArgs a) {
   static_assert(STAGES >= 3, "need a stage in store and a stage in refill besides the loads in flight");
   constexpr int LAG = STAGES - 2;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -290,11 +303,14 @@ __global__ void __maxnreg__(40) gather_tma_kernel(const GatherArgs a) {
     if (id < 0 || !a.cache.directory || id >= a.cache.num_nodes) return LG_CACHEMISS_FLAG;
     return ld_nc_s32_hint(a.cache.directory + id, keep);
   };
-  auto form_ptr = [&](int32_t id, int32_t gidx) -> const float* {
+  // *lrow: the row's index inside the local shard, or -1 when it lives elsewhere (peer shard, backing matrix)
+  auto form_ptr = [&](int32_t id, int32_t gidx, int32_t* lrow) -> const float* {
+    *lrow = -1;
     if (id < 0) return nullptr;  // -1 padding / out of range rows are skipped (cache_impl.cuh:263-264)
     if (identity) {
       t0++;
-      return a.cache.shard[a.local_part] + (int64_t)(id % a.cache.num_nodes) * a.cache.dim;
+      *lrow = (int32_t)(id % a.cache.num_nodes);
+      return a.cache.shard[a.local_part] + (int64_t)*lrow * a.cache.dim;
     }
     if (gidx < 0) {              // miss -> backing matrix (cache_impl.cuh:262-266)
       t2++;
@@ -306,7 +322,12 @@ __global__ void __maxnreg__(40) gather_tma_kernel(const GatherArgs a) {
     }
     const int32_t didx = gidx / a.cache.shard_rows;  // cache_impl.cuh:259-260
     const int32_t fidx = gidx - didx * a.cache.shard_rows;
-    if (didx == a.local_part) t0++; else t1++;
+    if (didx == a.local_part) {
+      t0++;
+      *lrow = fidx;
+    } else {
+      t1++;
+    }
     return a.cache.shard[didx] + (int64_t)fidx * a.cache.dim;
   };
   int tile0 = claim();
@@ -318,7 +339,8 @@ __global__ void __maxnreg__(40) gather_tma_kernel(const GatherArgs a) {
     const int tile2 = tile1 >= 0 ? claim() : -1;
     const int32_t id2 = load_id(tile2);
     const int32_t loc1 = load_loc(id1);
-    const float* src = form_ptr(id0, loc0);
+    int32_t lrow;
+    const float* src = form_ptr(id0, loc0, &lrow);
     if (tile0 >= 0) {
       const int s = (int)(it % STAGES);
       // stage s was read by the store of tile(it - STAGES), issued two iterations ago: only the
@@ -333,7 +355,24 @@ __global__ void __maxnreg__(40) gather_tma_kernel(const GatherArgs a) {
         mbar_expect_tx(bar, row_bytes * (uint32_t)__popc(valid));
       }
       __syncwarp();
-      if (src) bulk_g2s(smem_u32(smem + (size_t)s * stage_bytes + (size_t)lane * row_bytes), src, row_bytes, bar, pol_ld);
+      const uint32_t stage = smem_u32(smem + (size_t)s * stage_bytes);
+      if (a.use_g4) {
+        // a group of 4 consecutive rows of the tile that all live in the local shard is ONE tensor copy issued by the
+        // group's first lane (a quarter of the per-row UBLKCP issue chains); any other group moves row by row
+        const unsigned lmask = __ballot_sync(0xffffffffu, lrow >= 0);
+#pragma unroll
+        for (int g = 0; g < kTmaRows / 4; g++) {
+          if (((lmask >> (4 * g)) & 0xFu) == 0xFu) {
+            const int32_t r0 = __shfl_sync(0xffffffffu, lrow, 4 * g), r1 = __shfl_sync(0xffffffffu, lrow, 4 * g + 1),
+                          r2 = __shfl_sync(0xffffffffu, lrow, 4 * g + 2), r3 = __shfl_sync(0xffffffffu, lrow, 4 * g + 3);
+            if (lane == 4 * g) tensor_gather4(stage + (uint32_t)(4 * g) * row_bytes, &a.tmap, r0, r1, r2, r3, bar, pol_ld);
+          } else if ((lane >> 2) == g && src) {
+            bulk_g2s(stage + (uint32_t)lane * row_bytes, src, row_bytes, bar, pol_ld);
+          }
+        }
+      } else if (src) {
+        bulk_g2s(stage + (uint32_t)lane * row_bytes, src, row_bytes, bar, pol_ld);
+      }
       n_issued = it + 1;
     }
     tile0 = tile1;
@@ -403,6 +442,87 @@ static const Tune& tune() {
   return t;
 }
 
+// ---- tile::gather4: the tensor map over the local shard -------------------------------------------------------------
+// LG_GATHER4: 0 = per-row bulk copies only, 1 (default) = tensor gathers where they apply.  They apply when the local shard can be
+// described as a 2-D fp32 tensor whose 4-row groups keep shared memory 128-byte aligned (dim % 8 == 0), a row fits one box
+// (dim <= 256 elements) and the table has fewer than 2^31 rows.  The driver entry point comes from cudaGetDriverEntryPoint
+// (no link-time dependency on libcuda, like the VMM calls in runtime.cu).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+static int gather4_mode() {  // read per launch (a getenv, ~0.1 us) so that a process can switch it, e.g. the tests
+  const char* e = getenv("LG_GATHER4");
+  return e ? atoi(e) : 1;
+}
+static int gather4_promotion() {
+  static int m = [] {
+    const char* e = getenv("LG_GATHER4_PROMO");  // 0 none, 1 64 B, 2 128 B, 3 256 B
+    return e ? atoi(e) : 2;
+  }();
+  return m;
+}
+// fills a->tmap / a->use_g4; never fails the launch: without a tensor map the rows move one bulk copy each
+static void setup_gather4(GatherArgs* a) {
+  a->use_g4 = 0;
+  memset(&a->tmap, 0, sizeof(a->tmap));
+  if (gather4_mode() == 0) return;
+  const lg_feature_cache& c = a->cache;
+  const bool identity = (c.flags & LG_CACHE_IDENTITY) != 0;
+  if (a->local_part < 0 || a->local_part >= LG_MAX_DEVICE) return;
+  if (!identity && (!c.directory || a->local_part >= c.n_parts)) return;
+  const float* base = c.shard[a->local_part];
+  const int64_t rows = identity ? c.num_nodes : (int64_t)c.shard_rows;
+  if (!base || rows <= 0 || rows >= (1ll << 31) || c.dim % 8 != 0 || c.dim > 256 || ((uintptr_t)base & 15)) return;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return;
+  struct Cached {
+    const float* base;
+    int64_t rows;
+    int32_t dim, promo;
+    CUtensorMap map;
+  };
+  static thread_local Cached cache[8] = {};
+  static thread_local int next = 0;
+  const int promo = gather4_promotion();
+  for (const Cached& k : cache)
+    if (k.base == base && k.rows == rows && k.dim == c.dim && k.promo == promo) {
+      a->tmap = k.map;
+      a->use_g4 = 1;
+      return;
+    }
+  const cuuint64_t gdim[2] = {(cuuint64_t)c.dim, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)c.dim * 4};  // bytes between rows
+  const cuuint32_t box[2] = {(cuuint32_t)c.dim, 1};       // gather mode: one row per index, four indices per copy
+  const cuuint32_t estride[2] = {1, 1};
+  const CUtensorMapL2promotion l2p = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                     : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                  : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  CUtensorMap m;
+  if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return;
+  Cached& slot = cache[next++ % 8];
+  slot.base = base;
+  slot.rows = rows;
+  slot.dim = c.dim;
+  slot.promo = promo;
+  slot.map = m;
+  a->tmap = m;
+  a->use_g4 = 1;
+}
+
 template <int STAGES, int ROWS>
 int launch_tma(cudaStream_t st, const GatherArgs& a, int64_t max_rows) {
   const size_t smem = (size_t)a.cache.dim * 4 * ROWS * STAGES;
@@ -452,6 +572,7 @@ int launch_ldg(cudaStream_t st, const GatherArgs& a, int64_t max_rows, bool vec_
 
 int launch_gather(cudaStream_t st, GatherArgs a, int variant, int64_t max_rows) {
   const int dim = a.cache.dim;
+  setup_gather4(&a);
   LG_REQUIRE(max_rows < (1ll << 31), "gather: %lld rows in one launch (tile indices are 32-bit)", (long long)max_rows);
   const bool vec_ok = (dim % 4 == 0) && (((uintptr_t)a.dst & 15) == 0) && (((uintptr_t)a.cache.backing & 15) == 0);
   const Tune& t = tune();

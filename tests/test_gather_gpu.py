@@ -22,10 +22,17 @@ def _gather(rig, ids, variant, tier=None):
     return out.cpu().numpy()
 
 
+@pytest.fixture(params=["1", "0"], ids=["gather4", "rowwise"])
+def gather4(request, monkeypatch):
+    """the TMA mover with and without tile::gather4 tensor copies (LG_GATHER4, read per launch)"""
+    monkeypatch.setenv("LG_GATHER4", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("variant", [capi.GATHER_LDG, capi.GATHER_TMA])
 @pytest.mark.parametrize("dim", [100, 128, 256, 4, 3, 130])
 @pytest.mark.parametrize("host_features", [False, True])
-def test_gather_bit_exact(oracle, variant, dim, host_features):
+def test_gather_bit_exact(oracle, variant, dim, host_features, gather4):
     indptr, indices = small_graph(1500, 6.0, 50)
     N = len(indptr) - 1
     feat = synth.features(0, N, dim, 77)
@@ -192,3 +199,43 @@ def test_identity_cache_needs_no_directory(dim):
         assert (got[~ok] == 7.0).all()
         assert tiers.cpu().tolist() == [int(ok.sum()), 0, 0]
     dp.close()
+
+
+@pytest.mark.parametrize("promo", [0, 2, 3])
+@pytest.mark.parametrize("dim", [128, 256, 8, 104, 100])
+def test_gather4_tensor_copies(monkeypatch, dim, promo):
+    """LG_GATHER4=1: groups of 4 rows that all live in the local shard move as one cp.async.bulk.tensor tile::gather4
+    (identity placement and a fully cached directory placement); -1 holes, a ragged last tile and dims the tensor path
+    does not take (100: 4 rows are not a multiple of 128 bytes) fall back to per-row copies inside the same launch"""
+    from legion_b200.runner import DataPath
+    monkeypatch.setenv("LG_GATHER4", "1")
+    monkeypatch.setenv("LG_GATHER4_PROMO", str(promo))
+    N = 40000
+    feat = synth.features(0, N, dim, 9)
+    d_feat = torch.from_numpy(feat).cuda()
+    rng = np.random.default_rng(dim + promo)
+    for placement in ("identity", "directory"):
+        dp = DataPath(0, [2], 8, N, dim)
+        dp.set_backing_features(d_feat.data_ptr(), keep=[d_feat])
+        if placement == "identity":
+            dp.build_feature_cache_identity()
+        else:
+            hot = torch.from_numpy(rng.integers(0, 1000, N).astype(np.int64)).cuda()
+            order, _ = dp.rank_hotness(hot)
+            dp.build_feature_cache(order, cap=N - 5000)  # 12 % of the rows miss: mixed groups
+        for n in (3, 8, 33, 20001):
+            ids = rng.integers(0, N, n).astype(np.int32)
+            if n > 40:
+                ids[::61] = -1
+            d_ids = torch.from_numpy(ids).cuda()
+            out = torch.full((n, dim), 7.0, dtype=torch.float32, device="cuda")
+            tiers = torch.zeros(3, dtype=torch.int64, device="cuda")
+            capi.check(dp.L.lg_gather_rows(dp._stream(), C.byref(dp.cache), C.c_void_p(d_ids.data_ptr()), n,
+                                           C.c_void_p(out.data_ptr()), 0, capi.GATHER_TMA, C.c_void_p(tiers.data_ptr())))
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            ok = ids >= 0
+            assert np.array_equal(got[ok].view(np.uint32), feat[ids[ok]].view(np.uint32)), (placement, n)
+            assert (got[~ok] == 7.0).all()
+            assert int(tiers.sum().item()) == int(ok.sum())
+        dp.close()
