@@ -534,9 +534,27 @@ __device__ __forceinline__ bool rank_tile(const RankArgs& a, const RankHop& h, c
           sl[k] = map_home(a.map, (uint32_t)w[k]);
           cur[k] = (p0 + c + k < E) ? ld_ca_u64_hint(a.map.table + sl[k], keep) : 0ull;
         }
+        // continuations (the home slot holds another key) advance in lockstep: every pending probe chain of the thread
+        // issues its next load before any of them is waited for — finished one after the other, the chains of a thread's
+        // 8 edges added up, and the slowest thread of the CTA (the block scan waits for it) took 12 us per tile
+        // (profiles/r02u_rank_lockstep.md)
+        unsigned pend = 0;
 #pragma unroll
         for (int k = 0; k < CH; k++)
-          q[k] = (p0 + c + k < E) ? table_find_finish(a.map, (uint32_t)w[k], &sl[k], cur[k], keep) : 0u;
+          if (p0 + c + k < E && (uint32_t)(cur[k] >> 32) != (uint32_t)w[k] && cur[k] != kSlotEmpty) pend |= 1u << k;
+        while (pend) {
+#pragma unroll
+          for (int k = 0; k < CH; k++)
+            if (pend & (1u << k)) {
+              sl[k] = (sl[k] + 1) & a.map.mask;
+              cur[k] = ld_ca_u64_hint(a.map.table + sl[k], keep);
+            }
+#pragma unroll
+          for (int k = 0; k < CH; k++)
+            if ((pend & (1u << k)) && ((uint32_t)(cur[k] >> 32) == (uint32_t)w[k] || cur[k] == kSlotEmpty)) pend &= ~(1u << k);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k++) q[k] = (p0 + c + k < E) ? (uint32_t)cur[k] : 0u;
       } else {
 #pragma unroll
         for (int k = 0; k < CH; k++) q[k] = (p0 + c + k < E) ? ld_ca_u32_hint(a.map.pm + w[k], keep) : 0u;
@@ -559,6 +577,27 @@ __device__ __forceinline__ bool rank_tile(const RankArgs& a, const RankHop& h, c
     if (tid == 0 && tile == n_tiles - 1) h.hs->new_nodes = excl + total;  // C_h (:263)
     if (tid == 0) trace_mark(a.trace, tslot, tile, 3);
     int32_t local = node_base + excl + mine;
+    if (!PUBLISH) {
+      // last hop: nothing goes back into the map, so the first occurrences only need their vertex ids again — re-read as
+      // vectors up front (cached) and consumed by predicated straight-line code; the loop below re-reads one vertex per
+      // iteration, a chain of up to ITEMS dependent loads (3.3 us per tile in the trace)
+      int32_t wv[ITEMS];
+#pragma unroll
+      for (int k = 0; k < ITEMS; k += 4) {
+        const int4 v = *reinterpret_cast<const int4*>(h.gid + p0 + k);
+        wv[k] = v.x; wv[k + 1] = v.y; wv[k + 2] = v.z; wv[k + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++) {
+        if (mask & (1u << k)) {
+          if (local < a.ids_cap) a.ids[local] = wv[k];  // :270
+          else *a.status = 1;
+          if (h.agg_src) h.agg_src[edge_base + p0 + k] = local;
+          local++;
+        }
+      }
+      mask = 0;
+    }
     while (mask) {  // first occurrences, in edge order; the vertex is re-read (coalesced, cached) rather than kept
       const int k = __ffs(mask) - 1;
       mask &= mask - 1;
