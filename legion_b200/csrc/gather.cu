@@ -8,8 +8,10 @@
 // 16-byte vectors.  Two data movers:
 //   LDG  — warp per row, R rows in flight per warp, ld.global.nc.L1::no_allocate.v4 -> st.global.v4
 //   TMA  — one warp per CTA; every lane issues a cp.async.bulk (row -> shared memory stage,
-//          mbarrier complete_tx), lane 0 drains a finished stage with ONE bulk store of the
-//          32 contiguous destination rows.  No registers touch the payload (SASS: UBLKCP).
+//          mbarrier complete_tx) — or, for 4 rows that all live in the local shard, one lane issues ONE
+//          cp.async.bulk.tensor tile::gather4 over the shard's tensor map —, lane 0 drains a finished stage
+//          with ONE bulk store of the tile's contiguous destination rows.  No registers touch the payload
+//          (SASS: UBLKCP, UTMALDG.2D.GATHER4).
 // Values are moved bit-for-bit (no arithmetic), so the output is bit-exact by construction.
 #include <cuda.h>
 
@@ -251,12 +253,14 @@ __global__ void __maxnreg__(40) gather_tma_kernel(const __grid_constant__ Gather
   __shared__ int s_tileidx[STAGES];
 
   // Tile order.  A CTA works on chunks of a.chunk consecutive tiles (consecutive ids, consecutive destination rows).
-  // Static: chunk k of CTA b is b + k * gridDim.x.  Dynamic (a.ticket): a CTA's first chunk is its block index, every later
-  // one comes from a global counter
-  // whose atomicAdd is issued a whole chunk BEFORE its result is needed (the first version claimed every tile with a
-  // returning atomic and waited for it: half the bandwidth) — a CTA that starts late (its SM still busy with another
-  // kernel's CTAs) or whose warp gets fewer issue slots simply ends up moving fewer tiles instead of holding the whole
-  // launch back with a fixed share.  Claims are monotone: once one fails, every later one would fail too.
+  // Static (default, chunk = 1): chunk k of CTA b is b + k * gridDim.x.  Dynamic (a.ticket): a CTA's first chunk is its
+  // block index, every later one comes from a global counter whose atomic is issued a whole chunk BEFORE its result is
+  // needed — a CTA that starts late (its SM still busy with another kernel's CTAs) or whose warp gets fewer issue slots
+  // simply ends up moving fewer tiles instead of holding the whole launch back with a fixed share.  Claims are monotone:
+  // once one fails, every later one would fail too.  Measured (profiles/r02t_gather_tile_order.md): alone the launch goes
+  // from 0.90-0.92 to 0.96 of the HBM peak with 4 tiles per claim, next to the sampler's kernels it is slower than the
+  // static order, which therefore stays the default; one claim per tile is bound by the counter (one address takes
+  // ~0.35 G atomics/s).
   // (tile indices are 32-bit: a launch moves fewer than 2^31 ROWS, checked by the host)
   const int nt = (int)n_tiles, grid = (int)gridDim.x;
   int chunk = a.chunk > 0 ? a.chunk : 1;
