@@ -689,6 +689,12 @@ def roofline_of(c, res, hbm_peak, peak_kind, traffic_key):
               "kernel": f"feature gather ({res['gather_launches_per_step']} launch(es) per step)",
               "algorithmic_bytes_per_step": alg, "rows_per_step": rows, "gather_ms_per_step": res["gather_ms_per_step"],
               "hbm_algorithmic": hbm, "hit_mix": mix})
+    # the same algorithmic bytes over the WHOLE pipelined step of this rank: what the gather gets while the sampler's
+    # kernels of the other batches in flight share the GPU with it (achieved / frac above are the gather launch alone)
+    step_s = res["ms_per_step"] * 1e-3
+    if step_s > 0:
+        r["in_pipelined_step"] = {"hbm_algorithmic_GBps": alg / step_s / 1e9, "frac_of_hbm_peak": alg / step_s / 1e9 / hbm_peak,
+                                  "note": "8D+8 bytes per gathered row over ms_per_step (gather + sampler chain of the batches in flight)"}
     return r
 
 
