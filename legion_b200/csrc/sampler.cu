@@ -537,7 +537,7 @@ __device__ __forceinline__ bool rank_tile(const RankArgs& a, const RankHop& h, c
         // continuations (the home slot holds another key) advance in lockstep: every pending probe chain of the thread
         // issues its next load before any of them is waited for — finished one after the other, the chains of a thread's
         // 8 edges added up, and the slowest thread of the CTA (the block scan waits for it) took 12 us per tile
-        // (profiles/r02u_rank_lockstep.md)
+        // (profiles/r02v_rank_lockstep.md)
         unsigned pend = 0;
 #pragma unroll
         for (int k = 0; k < CH; k++)
